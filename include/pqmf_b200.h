@@ -1,0 +1,112 @@
+/*
+ * pqmf_b200 -- C ABI of the B200-native PQMF analysis / synthesis engine.
+ *
+ * This header is the drop-in boundary for the reference's hot path.  The reference
+ * (oviniciuscesar/Pseudo-Quadrature-Mirror-Filter) has no FFI of its own: its boundary is
+ * the Python module API of pqmf.py (class PQMF pqmf.py:202-288, class CachedPQMF
+ * pqmf.py:306-354).  Each entry point below replaces the arithmetic behind one of those
+ * methods; the Python mirror in pqmf_b200/pqmf.py (and the TORCH_LIBRARY ops in
+ * csrc/torch_ops.cpp) call exactly these symbols and nothing else.  INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer to row-contiguous float32 unless the name ends
+ *     in _host; the caller owns all buffers (including streaming state);
+ *   - functions never allocate device memory, never synchronise, never throw: they enqueue
+ *     on `stream` (a cudaStream_t passed as void*) and return 0 on success, a negative
+ *     PQMF_ERR_* code for rejected arguments, or a positive cudaError_t value;
+ *   - M = n_band, L = hk.shape[1] (prototype length centre-padded to a power of two,
+ *     pqmf.py:26-32), hk is the registered buffer `hk` [M, L] (pqmf.py:230);
+ *   - sign mask sigma(k, n) = -1 iff band k is odd and GLOBAL frame index n is even
+ *     (reverse_half, pqmf.py:13-22); `frame_parity` is (global index of the first frame) & 1.
+ */
+#ifndef PQMF_B200_H_
+#define PQMF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQMF_B200_ABI_VERSION 1
+
+#define PQMF_OK 0
+#define PQMF_ERR_ARG (-1)         /* null pointer, non-positive size, misaligned buffer ...      */
+#define PQMF_ERR_UNSUPPORTED (-2) /* combination the library has no kernel for                    */
+#define PQMF_ERR_NO_DEVICE (-3)   /* no CUDA device / wrong architecture (needs sm_100)          */
+
+/* flags */
+#define PQMF_FLAG_EXACT 1u   /* force the direct-form kernels (bit-faithful to the registered hk)      */
+#define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
+                              * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
+
+typedef void* pqmf_stream_t; /* cudaStream_t */
+
+int pqmf_abi_version(void);
+const char* pqmf_strerror(int code);
+
+/* Which kernel family a call with these parameters would use: 0 = direct form (generic),
+ * 1 = fold + tensor-core modulation fast path (n_band 16, L 512).  `tables` may be NULL. */
+int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
+
+/* ---- coefficient tables for the fast path (host side, one-off; replaces nothing in the reference:
+ *      the reference re-derives its polyphase weights on every call, pqmf.py:128, :148-149) ----
+ * Factorises hk[k, r + 2M q] ~= g[r + 2M q] * C[k, r] from the fp32 prototype h
+ * (buffer `h`, pqmf.py:231) and returns the largest |hk - g (x) C| in *residual (may be NULL).
+ * tables_host must hold pqmf_tables_numel(M, L) floats: [ g (L) | C_hi (M*2M) | C_lo (M*2M) ].
+ * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path. */
+long pqmf_tables_numel(int M, int L);
+int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
+                          double* residual);
+
+/* ---- offline analysis: PQMF.forward (pqmf.py:247-259 -> polyphase_forward :115-130 /
+ *      classic_forward :160-177, then reverse_half) and CachedPQMF.forward (:339-343) ----
+ *   y[b,k,n] = sigma(k,n) * sum_j hk[k,j] * x[b, n*M + j - L/2],  x = 0 outside [0,T), 0 <= n < n_frames
+ * x [B, T] -> y [B, M, n_frames].  n_frames = T/M (polyphase; requires T % M == 0 there),
+ * floor(T/M) (classic) or ceil(T/M) (cached) -- the caller chooses. */
+int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* tables, int B, long T, long n_frames, int M,
+                      int L, unsigned flags, pqmf_stream_t stream);
+
+/* ---- offline synthesis: PQMF.inverse (pqmf.py:272-288 -> reverse_half, polyphase_inverse :133-157 /
+ *      classic_inverse :180-199) with delay_frames = 0, CachedPQMF.inverse (:345-354) with 1 ----
+ *   out[b,tau] = M * sum_k sum_n sigma(k,n) s[b,k,n] * hk[k, tau - n*M + L/2 - delay_frames*M]
+ * s [B, M, n_frames] -> out [B, M*n_frames]. */
+int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float* tables, int B, long n_frames, int M, int L,
+                       int delay_frames, unsigned flags, pqmf_stream_t stream);
+
+/* ---- streaming (cached) mode: what cached_conv's cached padding does for the two layers
+ *      CachedPQMF builds at pqmf.py:316-333, with explicit caller-owned state ----
+ * analysis: frame n of the block sees samples [n*M - L, n*M) of (history ++ x):
+ *   y[b,k,n] = sigma(k, n + frame_parity) * sum_j hk[k,j] * X[b, n*M + j - L]
+ * state_in  [B, L]: the L samples that preceded x (zeros at stream start)
+ * state_out [B, L]: the last L samples of (state_in ++ x); must not alias state_in.
+ * T % M must be 0. */
+int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const float* tables, const float* state_in,
+                             float* state_out, int B, long T, int M, int L, int frame_parity, unsigned flags,
+                             pqmf_stream_t stream);
+
+/* synthesis: output frame f of the block uses sub-band frames f-K .. f-1 of (history ++ s), K = L/M:
+ *   out[b,tau] = M * sum_k sum_n sigma(k, n + frame_parity) S[b,k,n] * hk[k, tau - n*M - M]
+ * state_in / state_out [B, M, K]: the K frames that preceded s / the last K frames of (state_in ++ s). */
+int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const float* tables, const float* state_in,
+                              float* state_out, int B, long n_frames, int M, int L, int frame_parity, unsigned flags,
+                              pqmf_stream_t stream);
+
+/* ---- end-to-end host entry (what a non-torch host -- e.g. the Pure Data external that loads the
+ *      reference's .ts, README.md:16 -- would call): host buffers in, host buffers out.
+ * Pipelines H2D copy, analysis, synthesis and D2H copy over row chunks on internal streams and
+ * synchronises before returning.  x_host [B, T] -> y_host [B, M, T/M] (may be NULL) and
+ * out_host [B, T].  Pinned host buffers give full PCIe bandwidth; pageable ones work. */
+int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
+                            const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
+                            int device);
+
+/* Number of kernels the library has launched in this process (bench.py reports it as gpu_launches). */
+unsigned long long pqmf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQMF_B200_H_ */

@@ -1,0 +1,315 @@
+// pqmf_b200 C ABI (include/pqmf_b200.h): argument checking, kernel selection, launches.
+// No torch types, no allocation on the device-pointer entry points, no synchronisation.
+#include "../../include/pqmf_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "direct_form.cuh"
+#include "fast16.cuh"
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+
+inline int log2_exact(int v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+inline int cuda_status() {
+  cudaError_t e = cudaGetLastError();
+  return (int)e;
+}
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return (int)e;
+}
+
+// ------------------------------------------------------------------ direct-form launches
+template <int BG, int RF>
+int launch_analysis_direct(pqmf::AnalysisDirectParams p, int B, cudaStream_t st) {
+  constexpr int FL = pqmf::kDirectThreads / BG, FT = FL * RF, NB = 4 * BG;
+  p.xstride = (FT + p.QC - 1) | 1;
+  const size_t smem = ((size_t)p.JC * NB + (size_t)p.M * p.xstride) * sizeof(float);
+  if (smem > 200 * 1024) return PQMF_ERR_UNSUPPORTED;
+  auto kern = pqmf::analysis_direct_kernel<BG, RF>;
+  if (int e = ensure_smem(kern, smem)) return e;
+  dim3 grid((unsigned)((p.n_frames + FT - 1) / FT), (unsigned)((p.M + NB - 1) / NB), (unsigned)B);
+  kern<<<grid, pqmf::kDirectThreads, smem, st>>>(p);
+  ++g_launches;
+  return cuda_status();
+}
+
+int analysis_direct(const float* x, const float* hist, float* y, const float* hk, int B, long T, long n_frames, int M, int L,
+                    int off, int parity, int nosign, cudaStream_t st) {
+  if (n_frames == 0 || B == 0) return PQMF_OK;
+  pqmf::AnalysisDirectParams p{};
+  p.x = x; p.hist = hist; p.y = y; p.hk = hk;
+  p.T = T; p.n_frames = n_frames; p.M = M; p.L = L; p.off = off; p.parity = parity & 1; p.nosign = nosign;
+  p.m_shift = log2_exact(M);
+  int jc = (512 / M) * M;
+  if (jc < M) jc = M;
+  const int lceil = ((L + M - 1) / M) * M;
+  if (jc > lceil) jc = lceil;
+  p.JC = jc; p.QC = jc / M;
+  if (B > 65535) return PQMF_ERR_UNSUPPORTED;
+  if (M <= 4) return launch_analysis_direct<1, 4>(p, B, st);
+  if (M <= 8) return launch_analysis_direct<2, 4>(p, B, st);
+  if (M <= 32) return launch_analysis_direct<4, 4>(p, B, st);
+  if (M <= 64) return launch_analysis_direct<4, 2>(p, B, st);
+  return launch_analysis_direct<4, 1>(p, B, st);
+}
+
+template <int PG, int RF, bool VEC>
+int launch_synthesis_direct(pqmf::SynthesisDirectParams p, int B, cudaStream_t st) {
+  constexpr int FL = pqmf::kDirectThreads / PG, FT = FL * RF, NP = 4 * PG;
+  p.hstride = p.ND * p.M + 16;
+  p.sstride = (FT + p.ND - 1) | 1;
+  const size_t smem = (size_t)pqmf::kSynthBandsPerChunk * ((size_t)p.hstride + p.sstride) * sizeof(float);
+  if (smem > 200 * 1024) return PQMF_ERR_UNSUPPORTED;
+  auto kern = pqmf::synthesis_direct_kernel<PG, RF, VEC>;
+  if (int e = ensure_smem(kern, smem)) return e;
+  dim3 grid((unsigned)((p.F + FT - 1) / FT), (unsigned)((p.M + NP - 1) / NP), (unsigned)B);
+  kern<<<grid, pqmf::kDirectThreads, smem, st>>>(p);
+  ++g_launches;
+  return cuda_status();
+}
+
+int synthesis_direct(const float* s, const float* hist, float* out, const float* hk, int B, long F, int M, int L, int off2,
+                     int parity, int nosign, cudaStream_t st) {
+  if (F == 0 || B == 0) return PQMF_OK;
+  pqmf::SynthesisDirectParams p{};
+  p.s = s; p.hist = hist; p.out = out; p.hk = hk;
+  p.F = F; p.M = M; p.L = L; p.K = L / M; p.off2 = off2; p.parity = parity & 1; p.nosign = nosign;
+  p.dlo = (int)pqmf::floor_div(-(long)off2, M);
+  const int dhi = (int)pqmf::floor_div((long)L - 1 - off2, M);
+  p.ND = dhi - p.dlo + 1;
+  if (B > 65535) return PQMF_ERR_UNSUPPORTED;
+  const bool vec = (M % 4) == 0;
+  if (!vec) return launch_synthesis_direct<4, 4, false>(p, B, st);
+  if (M <= 4) return launch_synthesis_direct<1, 4, true>(p, B, st);
+  if (M <= 8) return launch_synthesis_direct<2, 4, true>(p, B, st);
+  return launch_synthesis_direct<4, 4, true>(p, B, st);
+}
+
+int roll_history(const float* old_h, const float* blk, float* new_h, long rows, int W, long Tb, cudaStream_t st) {
+  const long n = rows * W;
+  if (n == 0) return PQMF_OK;
+  const int threads = 256;
+  pqmf::roll_history_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(old_h, blk, new_h, rows, W, Tb);
+  ++g_launches;
+  return cuda_status();
+}
+
+bool bad_dims(int B, long n, int M, int L) { return B < 0 || n < 0 || M < 2 || L < M || L > (1 << 16); }
+
+bool use_fast(int M, int L, const float* tables, unsigned flags) {
+  return tables != nullptr && !(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_NO_SIGN)) && pqmf::fast16_supported(M, L);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pqmf_abi_version(void) { return PQMF_B200_ABI_VERSION; }
+
+const char* pqmf_strerror(int code) {
+  switch (code) {
+    case PQMF_OK: return "ok";
+    case PQMF_ERR_ARG: return "pqmf_b200: invalid argument (null pointer, bad size or misaligned buffer)";
+    case PQMF_ERR_UNSUPPORTED: return "pqmf_b200: unsupported parameter combination";
+    case PQMF_ERR_NO_DEVICE: return "pqmf_b200: no usable CUDA device (needs sm_100)";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pqmf_b200: unknown error";
+  }
+}
+
+unsigned long long pqmf_launch_count(void) { return g_launches.load(); }
+
+int pqmf_path_for(int M, int L, const float* tables, unsigned flags) { return use_fast(M, L, tables, flags) ? 1 : 0; }
+
+long pqmf_tables_numel(int M, int L) { return pqmf::fast16_supported(M, L) ? (long)L + 2L * M * 2 * M : 0; }
+
+int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
+                          double* residual) {
+  if (!hk_host || !h_host || !tables_host || N <= 0 || N > L) return PQMF_ERR_ARG;
+  if (!pqmf::fast16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
+  // hk[k, r + 2M q] = (-1)^q * 2 hpad[r + 2M q] * cos((2k+1) pi/(2M) (r - c0) + (-1)^k pi/4)   
+  //                 =  g[r + 2M q]              * C[k, r]
+  const int pad_l = (L - N) / 2;       // center_pad_next_pow_2, reference pqmf.py:26-32
+  const int c0 = pad_l + N / 2;        // column of the prototype centre
+  const int R = 2 * M;
+  float* g = tables_host;
+  float* chi = tables_host + L;
+  float* clo = chi + (size_t)M * R;
+  for (int j = 0; j < L; ++j) {
+    const int t = j - pad_l;
+    const float hv = (t >= 0 && t < N) ? h_host[t] : 0.f;
+    g[j] = ((j / R) & 1) ? -hv : hv;
+  }
+  const double pi = 3.14159265358979323846;
+  std::vector<double> C((size_t)M * R);
+  for (int k = 0; k < M; ++k)
+    for (int r = 0; r < R; ++r)
+      C[(size_t)k * R + r] = 2.0 * std::cos((2 * k + 1) * pi / (2.0 * M) * (r - c0) + ((k & 1) ? -pi / 4 : pi / 4));
+  // tf32 split: hi = round-to-nearest on 13 dropped mantissa bits, lo = tf32(C - hi)
+  auto tf32_rn = [](float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+  };
+  for (size_t i = 0; i < (size_t)M * R; ++i) {
+    const float hi = tf32_rn((float)C[i]);
+    chi[i] = hi;
+    clo[i] = tf32_rn((float)(C[i] - (double)hi));
+  }
+  double res = 0.0;
+  for (int k = 0; k < M; ++k)
+    for (int j = 0; j < L; ++j) {
+      const double model = (double)g[j] * C[(size_t)k * R + (j % R)];
+      res = std::fmax(res, std::fabs((double)hk_host[(size_t)k * L + j] - model));
+    }
+  if (residual) *residual = res;
+  return PQMF_OK;
+}
+
+int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* tables, int B, long T, long n_frames, int M,
+                      int L, unsigned flags, pqmf_stream_t stream) {
+  if (bad_dims(B, T, M, L) || n_frames < 0) return PQMF_ERR_ARG;
+  if (B == 0 || n_frames == 0) return PQMF_OK;
+  if (!x || !y || !hk) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_fast(M, L, tables, flags) && pqmf::fast16_analysis_ok(x, y, T, n_frames)) {
+    int e = pqmf::fast16_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, st);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  return analysis_direct(x, nullptr, y, hk, B, T, n_frames, M, L, L / 2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
+}
+
+int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float* tables, int B, long n_frames, int M, int L,
+                       int delay_frames, unsigned flags, pqmf_stream_t stream) {
+  if (bad_dims(B, n_frames, M, L) || delay_frames < 0 || delay_frames > 1) return PQMF_ERR_ARG;
+  if (B == 0 || n_frames == 0) return PQMF_OK;
+  if (!s || !out || !hk) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int off2 = L / 2 - delay_frames * M;
+  if (use_fast(M, L, tables, flags) && pqmf::fast16_synthesis_ok(s, out, n_frames)) {
+    int e = pqmf::fast16_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, st);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  return synthesis_direct(s, nullptr, out, hk, B, n_frames, M, L, off2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
+}
+
+int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const float* tables, const float* state_in,
+                             float* state_out, int B, long T, int M, int L, int frame_parity, unsigned flags,
+                             pqmf_stream_t stream) {
+  if (bad_dims(B, T, M, L) || (T % M) != 0) return PQMF_ERR_ARG;
+  if (B == 0) return PQMF_OK;
+  if (!hk || !state_in || !state_out || state_in == state_out) return PQMF_ERR_ARG;
+  if (T == 0) return PQMF_ERR_ARG;
+  if (!x || !y) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long F = T / M;
+  if (use_fast(M, L, tables, flags) && pqmf::fast16_analysis_ok(x, y, T, F)) {
+    int e = pqmf::fast16_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, st);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  int e = analysis_direct(x, state_in, y, hk, B, T, F, M, L, L, frame_parity, 0, st);
+  if (e) return e;
+  return roll_history(state_in, x, state_out, B, L, T, st);
+}
+
+int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const float* tables, const float* state_in,
+                              float* state_out, int B, long n_frames, int M, int L, int frame_parity, unsigned flags,
+                              pqmf_stream_t stream) {
+  if (bad_dims(B, n_frames, M, L) || (L % M) != 0) return PQMF_ERR_ARG;
+  if (B == 0) return PQMF_OK;
+  if (!hk || !state_in || !state_out || state_in == state_out || n_frames == 0) return PQMF_ERR_ARG;
+  if (!s || !out) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = L / M;
+  // history frames sit K frames before frame 0 of the block: their parity offset is (frame_parity - K)
+  if (use_fast(M, L, tables, flags) && pqmf::fast16_synthesis_ok(s, out, n_frames)) {
+    int e = pqmf::fast16_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, st);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  int e = synthesis_direct(s, state_in, out, hk, B, n_frames, M, L, -M, frame_parity, 0, st);
+  if (e) return e;
+  return roll_history(state_in, s, state_out, (long)B * M, K, n_frames, st);
+}
+
+int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
+                            const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
+                            int device) {
+  if (bad_dims(B, T, M, L) || !x_host || !out_host || !hk_host || (T % M) != 0) return PQMF_ERR_ARG;
+  if (B == 0 || T == 0) return PQMF_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return PQMF_ERR_NO_DEVICE;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  const long F = T / M;
+  // Row chunks sized ~32 MiB of input so that H2D(i+1), kernels(i) and D2H(i-1) overlap (PCIe is full duplex).
+  long rows_per_chunk = (32L << 20) / (T * (long)sizeof(float));
+  if (rows_per_chunk < 1) rows_per_chunk = 1;
+  if (rows_per_chunk > B) rows_per_chunk = B;
+  const int n_buf = 3;
+  const size_t chunk_elems = (size_t)rows_per_chunk * T;
+  const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
+  float *d_hk = nullptr, *d_tab = nullptr, *d_x[n_buf] = {}, *d_y[n_buf] = {}, *d_o[n_buf] = {};
+  cudaStream_t st[n_buf] = {};
+  int rc = PQMF_OK;
+  auto check = [&](cudaError_t err) { if (err != cudaSuccess && rc == PQMF_OK) rc = (int)err; return err == cudaSuccess; };
+  check(cudaMalloc(&d_hk, (size_t)M * L * sizeof(float)));
+  if (n_tab) check(cudaMalloc(&d_tab, (size_t)n_tab * sizeof(float)));
+  for (int i = 0; i < n_buf && rc == PQMF_OK; ++i) {
+    check(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    check(cudaMalloc(&d_x[i], chunk_elems * sizeof(float)));
+    check(cudaMalloc(&d_y[i], chunk_elems * sizeof(float)));
+    check(cudaMalloc(&d_o[i], chunk_elems * sizeof(float)));
+  }
+  if (rc == PQMF_OK) {
+    check(cudaMemcpy(d_hk, hk_host, (size_t)M * L * sizeof(float), cudaMemcpyHostToDevice));
+    if (n_tab) check(cudaMemcpy(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  int slot = 0;
+  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += rows_per_chunk, slot = (slot + 1) % n_buf) {
+    const int rows = (int)((B - r0 < rows_per_chunk) ? (B - r0) : rows_per_chunk);
+    const size_t n = (size_t)rows * T;
+    cudaStream_t s = st[slot];
+    check(cudaMemcpyAsync(d_x[slot], x_host + (size_t)r0 * T, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (rc) break;
+    rc = pqmf_analysis_f32(d_x[slot], d_y[slot], d_hk, d_tab, rows, T, F, M, L, flags, s);
+    if (rc) break;
+    rc = pqmf_synthesis_f32(d_y[slot], d_o[slot], d_hk, d_tab, rows, F, M, L, delay_frames, flags, s);
+    if (rc) break;
+    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * T, d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    check(cudaMemcpyAsync(out_host + (size_t)r0 * T, d_o[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < n_buf; ++i)
+    if (st[i]) check(cudaStreamSynchronize(st[i]));
+  for (int i = 0; i < n_buf; ++i) {
+    if (d_x[i]) cudaFree(d_x[i]);
+    if (d_y[i]) cudaFree(d_y[i]);
+    if (d_o[i]) cudaFree(d_o[i]);
+    if (st[i]) cudaStreamDestroy(st[i]);
+  }
+  if (d_hk) cudaFree(d_hk);
+  if (d_tab) cudaFree(d_tab);
+  return rc;
+}
+
+}  // extern "C"

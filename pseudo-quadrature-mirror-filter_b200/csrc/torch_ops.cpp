@@ -1,0 +1,157 @@
+// torch custom ops `pqmf_b200::*` -- the glue between the Python mirror of the reference API
+// (pqmf_b200/pqmf.py) and the C ABI (include/pqmf_b200.h).  Registered through the dispatcher
+// with schemas so that torch.jit.script(...) of a module holding CachedPQMF works and a saved
+// .ts loads wherever this library is loaded (the reference exports its wrappers that way:
+// PQMFWrapper.py:102-108, PitchShifterPvoc/1-PitchShifterWrapper.py:337-343).
+//
+// There is deliberately NO CPU kernel: the ops are registered for the CUDA dispatch key only,
+// so a CPU tensor raises "Could not run 'pqmf_b200::analysis' with arguments from the 'CPU'
+// backend" instead of silently falling back.
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include "../../include/pqmf_b200.h"
+
+namespace {
+
+void check_rc(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, what, " failed: ", pqmf_strerror(rc), " (code ", rc, ")");
+}
+
+void check_f32_cuda(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor (pqmf_b200 has no CPU fallback)");
+  TORCH_CHECK(t.scalar_type() == at::kFloat, name, " must be float32, got ", t.scalar_type());
+}
+
+const float* tables_ptr(const at::Tensor& tables, const at::Tensor& like) {
+  if (tables.numel() == 0) return nullptr;
+  check_f32_cuda(tables, "tables");
+  TORCH_CHECK(tables.is_contiguous() && tables.device() == like.device(), "tables must be contiguous and on the input's device");
+  return tables.data_ptr<float>();
+}
+
+struct Bank {
+  int64_t M, L;
+  const float* ptr;
+};
+
+Bank bank_of(const at::Tensor& hk, const at::Tensor& like) {
+  check_f32_cuda(hk, "hk");
+  TORCH_CHECK(hk.dim() == 2 && hk.is_contiguous(), "hk must be a contiguous [n_band, L] tensor");
+  TORCH_CHECK(hk.device() == like.device(), "hk and the input must be on the same device");
+  return {hk.size(0), hk.size(1), hk.data_ptr<float>()};
+}
+
+// x [B, C, T] -> [B, C*M, n_frames]      (reference: C == 1; C > 1 is folded into the batch)
+at::Tensor analysis(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, int64_t flags) {
+  check_f32_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 3, "pqmf analysis expects [batch, channels, time], got ", x.dim(), " dims");
+  const Bank bank = bank_of(hk, x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const at::Tensor xc = x.contiguous();
+  const int64_t B = xc.size(0) * xc.size(1), T = xc.size(2);
+  TORCH_CHECK(n_frames >= 0 && B < (1LL << 31), "bad sizes");
+  at::Tensor y = at::empty({xc.size(0), xc.size(1) * bank.M, n_frames}, xc.options());
+  if (y.numel() == 0) return y;
+  check_rc(pqmf_analysis_f32(xc.data_ptr<float>(), y.data_ptr<float>(), bank.ptr, tables_ptr(tables, x), (int)B, (long)T,
+                             (long)n_frames, (int)bank.M, (int)bank.L, (unsigned)flags,
+                             (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_analysis_f32");
+  return y;
+}
+
+// s [B, C*M, F] -> [B, C, M*F]
+at::Tensor synthesis(const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables, int64_t delay_frames, int64_t flags) {
+  check_f32_cuda(s, "s");
+  TORCH_CHECK(s.dim() == 3, "pqmf synthesis expects [batch, n_band, frames], got ", s.dim(), " dims");
+  const Bank bank = bank_of(hk, s);
+  TORCH_CHECK(s.size(1) % bank.M == 0, "sub-band tensor has ", s.size(1), " channels, expected a multiple of n_band=", bank.M);
+  c10::cuda::CUDAGuard guard(s.device());
+  const at::Tensor sc = s.contiguous();
+  const int64_t C = sc.size(1) / bank.M, B = sc.size(0) * C, F = sc.size(2);
+  TORCH_CHECK(B < (1LL << 31), "bad sizes");
+  at::Tensor out = at::empty({sc.size(0), C, bank.M * F}, sc.options());
+  if (out.numel() == 0) return out;
+  check_rc(pqmf_synthesis_f32(sc.data_ptr<float>(), out.data_ptr<float>(), bank.ptr, tables_ptr(tables, s), (int)B, (long)F,
+                              (int)bank.M, (int)bank.L, (int)delay_frames, (unsigned)flags,
+                              (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_synthesis_f32");
+  return out;
+}
+
+// streaming: state tensors are caller-owned ping-pong buffers; state_out is written in place.
+at::Tensor analysis_stream(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& state_in,
+                           at::Tensor state_out, int64_t frame_parity, int64_t flags) {
+  check_f32_cuda(x, "x");
+  check_f32_cuda(state_in, "state_in");
+  check_f32_cuda(state_out, "state_out");
+  TORCH_CHECK(x.dim() == 3, "pqmf streaming analysis expects [streams, channels, block], got ", x.dim(), " dims");
+  const Bank bank = bank_of(hk, x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const at::Tensor xc = x.contiguous();
+  const int64_t B = xc.size(0) * xc.size(1), T = xc.size(2);
+  TORCH_CHECK(T % bank.M == 0, "streaming block length ", T, " must be a multiple of n_band=", bank.M);
+  TORCH_CHECK(state_in.is_contiguous() && state_out.is_contiguous() && state_in.numel() == B * bank.L &&
+                  state_out.numel() == B * bank.L,
+              "analysis state must be two contiguous [streams, L] buffers (L=", bank.L, ", streams=", B, ")");
+  TORCH_CHECK(state_in.data_ptr() != state_out.data_ptr(), "state_in and state_out must not alias");
+  at::Tensor y = at::empty({xc.size(0), xc.size(1) * bank.M, T / bank.M}, xc.options());
+  if (B == 0) return y;
+  check_rc(pqmf_analysis_stream_f32(xc.data_ptr<float>(), y.data_ptr<float>(), bank.ptr, tables_ptr(tables, x),
+                                    state_in.data_ptr<float>(), state_out.data_ptr<float>(), (int)B, (long)T, (int)bank.M,
+                                    (int)bank.L, (int)(frame_parity & 1), (unsigned)flags,
+                                    (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_analysis_stream_f32");
+  return y;
+}
+
+at::Tensor synthesis_stream(const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& state_in,
+                            at::Tensor state_out, int64_t frame_parity, int64_t flags) {
+  check_f32_cuda(s, "s");
+  check_f32_cuda(state_in, "state_in");
+  check_f32_cuda(state_out, "state_out");
+  TORCH_CHECK(s.dim() == 3, "pqmf streaming synthesis expects [streams, n_band, frames], got ", s.dim(), " dims");
+  const Bank bank = bank_of(hk, s);
+  TORCH_CHECK(s.size(1) % bank.M == 0, "sub-band tensor has ", s.size(1), " channels, expected a multiple of n_band=", bank.M);
+  c10::cuda::CUDAGuard guard(s.device());
+  const at::Tensor sc = s.contiguous();
+  const int64_t C = sc.size(1) / bank.M, B = sc.size(0) * C, F = sc.size(2);
+  TORCH_CHECK(state_in.is_contiguous() && state_out.is_contiguous() && state_in.numel() == B * bank.L &&
+                  state_out.numel() == B * bank.L,
+              "synthesis state must be two contiguous [streams, n_band, L/n_band] buffers");
+  TORCH_CHECK(state_in.data_ptr() != state_out.data_ptr(), "state_in and state_out must not alias");
+  TORCH_CHECK(F > 0, "empty block");
+  at::Tensor out = at::empty({sc.size(0), C, bank.M * F}, sc.options());
+  if (B == 0) return out;
+  check_rc(pqmf_synthesis_stream_f32(sc.data_ptr<float>(), out.data_ptr<float>(), bank.ptr, tables_ptr(tables, s),
+                                     state_in.data_ptr<float>(), state_out.data_ptr<float>(), (int)B, (long)F, (int)bank.M,
+                                     (int)bank.L, (int)(frame_parity & 1), (unsigned)flags,
+                                     (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_synthesis_stream_f32");
+  return out;
+}
+
+int64_t launch_count() { return (int64_t)pqmf_launch_count(); }
+
+}  // namespace
+
+TORCH_LIBRARY(pqmf_b200, m) {
+  m.def("analysis(Tensor x, Tensor hk, Tensor tables, int n_frames, int flags) -> Tensor");
+  m.def("synthesis(Tensor s, Tensor hk, Tensor tables, int delay_frames, int flags) -> Tensor");
+  m.def(
+      "analysis_stream(Tensor x, Tensor hk, Tensor tables, Tensor state_in, Tensor(a!) state_out, int frame_parity, int flags) "
+      "-> Tensor");
+  m.def(
+      "synthesis_stream(Tensor s, Tensor hk, Tensor tables, Tensor state_in, Tensor(a!) state_out, int frame_parity, int flags) "
+      "-> Tensor");
+  m.def("launch_count() -> int", &launch_count);
+}
+
+TORCH_LIBRARY_IMPL(pqmf_b200, CUDA, m) {
+  m.impl("analysis", &analysis);
+  m.impl("synthesis", &synthesis);
+  m.impl("analysis_stream", &analysis_stream);
+  m.impl("synthesis_stream", &synthesis_stream);
+}

@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA path (through the C ABI and through the torch ops / module API) against the
+oracle and the reference-generated golden vectors.  Tolerance: north_star's max-abs <= 1e-5 against the
+reference's fp32 results, round-trip SNR within 0.1 dB."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pqmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # BASELINE.json north_star: max-abs error vs the reference's own fp32 PQMF
+
+
+@pytest.fixture(scope="module")
+def pq():
+    import pqmf_b200
+
+    return pqmf_b200
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pqmf_b200 import _lib
+
+    return _lib
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _tables_for(lib, hk, h):
+    tables, res = lib.build_tables(torch.from_numpy(hk), torch.from_numpy(h))
+    return tables.cuda() if tables.numel() else None
+
+
+# ------------------------------------------------------------------ raw C ABI (ctypes, device pointers)
+@pytest.mark.parametrize("m", (4, 8, 16, 32, 64))
+@pytest.mark.parametrize("exact", (True, False))
+def test_cabi_offline_vs_golden(golden, lib, m, exact):
+    g = golden(f"vectors_M{m}.npz")
+    bank = golden(f"bank_M{m}.npz")
+    hk, h = bank["hk"], bank["h"]
+    length = hk.shape[1]
+    x = g["x"][:, 0]
+    b, t = x.shape
+    d_x, d_hk = dev(x), dev(hk)
+    tables = None if exact else _tables_for(lib, hk, h)
+    flags = lib.PQMF_FLAG_EXACT if exact else 0
+    tp = tables.data_ptr() if tables is not None else None
+    y = torch.empty(b, m, t // m, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.cabi.pqmf_analysis_f32(d_x.data_ptr(), y.data_ptr(), d_hk.data_ptr(), tp, b, t, t // m, m, length, flags, st)
+    assert rc == 0, lib.strerror(rc)
+    torch.cuda.synchronize()
+    for key in ("y_poly", "y_classic", "y_cached"):
+        assert np.abs(y.cpu().numpy() - g[key]).max() <= TOL, key
+    # synthesis is fed the REFERENCE's sub-bands (SURVEY 8d parity protocol)
+    s = dev(g["y_poly"])
+    for delay, key in ((0, "out_poly"), (1, "out_cached")):
+        out = torch.empty(b, t, device="cuda")
+        rc = lib.cabi.pqmf_synthesis_f32(s.data_ptr(), out.data_ptr(), d_hk.data_ptr(), tp, b, t // m, m, length, delay, flags, st)
+        assert rc == 0, lib.strerror(rc)
+        torch.cuda.synchronize()
+        assert np.abs(out.cpu().numpy() - g[key][:, 0]).max() <= TOL, key
+
+
+def test_cabi_rejects_bad_arguments(lib):
+    c = lib.cabi
+    assert c.pqmf_analysis_f32(None, None, None, None, 1, 64, 4, 16, 512, 0, None) == -1
+    assert c.pqmf_analysis_f32(None, None, None, None, 1, 64, 4, 1, 512, 0, None) == -1
+    assert c.pqmf_synthesis_f32(None, None, None, None, 1, 4, 16, 512, 2, 0, None) == -1
+    assert c.pqmf_analysis_stream_f32(None, None, None, None, None, None, 1, 65, 16, 512, 0, 0, None) == -1
+    assert c.pqmf_analysis_f32(None, None, None, None, 0, 64, 4, 16, 512, 0, None) == 0  # empty batch is a no-op
+
+
+# ------------------------------------------------------------------ module API, offline
+@pytest.mark.parametrize("m", (4, 8, 16, 32, 64))
+@pytest.mark.parametrize("polyphase", (True, False))
+def test_module_matches_reference(golden, pq, m, polyphase):
+    g = golden(f"vectors_M{m}.npz")
+    mod = pq.PQMF(100, m, polyphase=polyphase).cuda()
+    assert np.abs(mod.hk.cpu().numpy() - golden(f"bank_M{m}.npz")["hk"]).max() <= 1e-8
+    x = dev(g["x"])
+    y = mod(x)
+    assert y.shape == (2, m, x.shape[-1] // m)
+    assert np.abs(y.cpu().numpy() - g["y_poly" if polyphase else "y_classic"]).max() <= TOL
+    out = mod.inverse(dev(g["y_poly"]))
+    assert out.shape == x.shape
+    assert np.abs(out.cpu().numpy() - g["out_poly" if polyphase else "out_classic"]).max() <= TOL
+    # round trip through our own sub-bands: SNR within 0.1 dB of the reference's round trip
+    rt = mod.inverse(y).cpu().numpy()
+    ref_rt = g["out_poly"]
+    assert abs(O.snr_db(g["x"], rt) - O.snr_db(g["x"], ref_rt)) <= 0.1
+
+
+@pytest.mark.parametrize("m", (4, 16, 64))
+def test_exact_mode_on_unit_variance_subbands(golden, pq, m):
+    g = golden(f"vectors_M{m}.npz")
+    mod = pq.PQMF(100, m, exact=True).cuda()
+    out = mod.inverse(dev(g["s_rand"]))
+    assert np.abs(out.cpu().numpy() - g["out_rand"]).max() <= TOL
+
+
+@pytest.mark.parametrize("m", (4, 8, 16, 32, 64))
+def test_cached_module_and_ragged_lengths(golden, pq, m):
+    g = golden(f"vectors_M{m}.npz")
+    mod = pq.CachedPQMF(100, m).cuda()
+    x = dev(g["x"])
+    assert np.abs(mod(x).cpu().numpy() - g["y_cached"]).max() <= TOL
+    assert np.abs(mod.inverse(dev(g["y_poly"])).cpu().numpy() - g["out_cached"]).max() <= TOL
+    tr = int(g["x_ragged_len"])
+    xr = x[..., :tr].contiguous()
+    yr = mod(xr)
+    assert yr.shape[-1] == -(-tr // m)
+    assert np.abs(yr.cpu().numpy() - g["yr_cached"]).max() <= TOL
+    classic = pq.PQMF(100, m, polyphase=False).cuda()
+    yc = classic(xr)
+    assert yc.shape[-1] == tr // m
+    assert np.abs(yc.cpu().numpy() - g["yr_classic"]).max() <= TOL
+    with pytest.raises(RuntimeError):
+        pq.PQMF(100, m).cuda()(xr)  # polyphase needs T % M == 0 (reference: einops error)
+
+
+def test_torchscript_archive_vectors(golden, pq):
+    g = golden("ts_M16.npz")
+    mod = pq.CachedPQMF(100, 16).cuda()
+    assert np.array_equal(mod.h.cpu().numpy(), g["h"])
+    assert tuple(mod.forward_conv.weight.shape) == tuple(g["fwd_weight_shape"])
+    assert np.abs(mod.inverse_conv.weight.cpu().numpy() - g["inv_weight"]).max() <= 1e-8
+    assert np.abs(mod(dev(g["x"])).cpu().numpy() - g["y"]).max() <= TOL
+    assert np.abs(mod.inverse(dev(g["y"])).cpu().numpy() - g["out"]).max() <= TOL
+
+
+def test_non_power_of_two_classic(golden, pq):
+    g = golden("vectors_M12_classic.npz")
+    with pytest.raises(AssertionError):
+        pq.PQMF(100, 12)
+    mod = pq.PQMF(100, 12, polyphase=False).cuda()
+    y = mod(dev(g["x"]))
+    assert np.abs(y.cpu().numpy() - g["y"]).max() <= TOL
+    # the reference's classic synthesis for L % M != 0 follows the same closed form
+    out = mod.inverse(dev(g["y"]))
+    assert np.abs(out.cpu().numpy() - g["out"]).max() <= TOL
+
+
+def test_free_functions_skip_the_sign_mask(golden, pq):
+    g = golden("vectors_M16.npz")
+    hk = dev(golden("bank_M16.npz")["hk"])
+    x = dev(g["x"])
+    y = pq.reverse_half(pq.polyphase_forward(x, hk))
+    assert np.abs(y.cpu().numpy() - g["y_poly"]).max() <= TOL
+    y2 = pq.reverse_half(pq.classic_forward(x, hk))
+    assert np.abs(y2.cpu().numpy() - g["y_classic"]).max() <= TOL
+    s = pq.reverse_half(dev(g["y_poly"]))
+    assert np.abs(pq.polyphase_inverse(s, hk).cpu().numpy() - g["out_poly"]).max() <= TOL
+    assert np.abs(pq.classic_inverse(s, hk).cpu().numpy() - g["out_classic"]).max() <= TOL
+    # pre-arranged filters (rearrange_filter=False) as the reference's callers may pass them
+    w = hk.reshape(16, 32, 16).permute(0, 2, 1).contiguous()
+    assert torch.equal(pq.polyphase_forward(x, w, rearrange_filter=False), pq.polyphase_forward(x, hk))
+    wi = hk.flip(-1).reshape(16, 32, 16).permute(2, 0, 1).contiguous()
+    assert torch.equal(pq.polyphase_inverse(s, wi, rearrange_filter=False), pq.polyphase_inverse(s, hk))
+
+
+def test_flute_config1(golden, pq):
+    """BASELINE config 1: audio/flute.wav, n_band 16, attenuation 100, batch 1, padded as the wrappers do."""
+    g = golden("flute_C1.npz")
+    n_pad = int(g["n_pad"])
+    x = np.zeros((1, 1, n_pad), np.float32)
+    x[0, 0, : g["pcm"].shape[0]] = g["pcm"].astype(np.float32) / 32768.0
+    mod = pq.PQMF(100, 16).cuda()
+    y = mod(dev(x))
+    out = mod.inverse(y)
+    yn, on = y.cpu().numpy(), out.cpu().numpy()
+    lo, hi = g["excerpt"]
+    assert np.abs(yn[:, :, lo // 16 : hi // 16] - g["y_excerpt"]).max() <= TOL
+    assert np.abs(yn[:, :, :64] - g["y_head"]).max() <= TOL
+    assert np.abs(on[:, :, lo:hi] - g["out_excerpt"]).max() <= TOL
+    assert np.abs(on[:, :, :1024] - g["out_head"]).max() <= TOL
+    assert np.abs(on[:, :, -1024:] - g["out_tail"]).max() <= TOL
+    assert abs(O.snr_db(x, on) - float(g["flute_M16"])) <= 0.1
+    # whole clip against the oracle
+    hk = golden("bank_M16.npz")["hk"]
+    y64 = O.analysis(x[:, 0], hk)
+    assert np.abs(yn - y64).max() <= TOL
+    assert np.abs(on[:, 0] - O.synthesis(yn, hk)).max() <= TOL
+    cached = pq.CachedPQMF(100, 16).cuda()
+    oc = cached.inverse(cached(dev(x))).cpu().numpy()
+    assert abs(O.snr_db(x[..., :-16], oc[..., 16:]) - float(g["flute_M16_cached_delay16"])) <= 0.1
+
+
+# ------------------------------------------------------------------ larger seeded inputs vs the oracle
+@pytest.mark.parametrize("m,b,t", ((16, 3, 65536), (16, 1, 16 * 4097), (16, 2, 2048), (16, 5, 48), (8, 2, 40000), (32, 2, 32768)))
+def test_against_oracle_various_shapes(golden, pq, m, b, t):
+    hk = golden(f"bank_M{m}.npz")["hk"]
+    x = O.audio_like((b, 1, t), 4242 + t)
+    mod = pq.PQMF(100, m).cuda()
+    y = mod(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0], hk)
+    assert np.abs(y - y64).max() <= TOL / 2
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
+
+
+def test_multichannel_is_folded_into_batch(golden, pq):
+    g = golden("flutemulti_excerpt.npz")
+    x = (g["pcm"].astype(np.float32) / 32768.0)[None]  # [1, 2, T]
+    mod = pq.PQMF(100, 16).cuda()
+    y = mod(dev(x))
+    assert y.shape == (1, 32, x.shape[-1] // 16)
+    y_rows = mod(dev(x.reshape(2, 1, -1)))
+    assert torch.equal(y.reshape(2, 16, -1), y_rows)
+    out = mod.inverse(y)
+    assert out.shape == x.shape
+
+
+def test_empty_and_tiny_inputs(pq):
+    mod = pq.PQMF(100, 16).cuda()
+    assert mod(torch.zeros(0, 1, 64, device="cuda")).shape == (0, 16, 4)
+    assert mod(torch.zeros(2, 1, 0, device="cuda")).shape == (2, 16, 0)
+    assert mod.inverse(torch.zeros(2, 16, 0, device="cuda")).shape == (2, 1, 0)
+    y = mod(torch.ones(1, 1, 16, device="cuda"))
+    assert y.shape == (1, 16, 1) and torch.isfinite(y).all()
+    one = pq.PQMF(100, 1, polyphase=False) if False else None  # n_band == 1 is an identity in the reference
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(4, 64, device="cuda"))  # 2-D input
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(1, 1, 64))  # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(1, 1, 64, device="cuda", dtype=torch.float64))
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_config2_properties_full_size(pq):
+    """BASELINE config 2 (64 x 2^20): linearity, shift covariance by 2M, near-perfect reconstruction."""
+    torch.manual_seed(0)
+    mod = pq.PQMF(100, 16).cuda()
+    b, t = 64, 1 << 20
+    x = (0.5 * torch.randn(b, 1, t, device="cuda")).clamp_(-1, 1)
+    y = mod(x)
+    out = mod.inverse(y)
+    err = out - x
+    snr = 10 * torch.log10((x[..., 4096:-4096] ** 2).sum() / (err[..., 4096:-4096] ** 2).sum())
+    assert snr.item() > 55.0  # interior SNR of the near-PR bank on noise (~60 dB)
+    x2 = torch.roll(x, 32, dims=-1)
+    y2 = mod(x2)
+    assert (y2[..., 40:-40] - torch.roll(y, 2, dims=-1)[..., 40:-40]).abs().max().item() <= 2e-6
+    a = mod(0.25 * x) - 0.25 * y
+    assert a.abs().max().item() <= 2e-6
+    # every batch row is processed independently and identically
+    assert torch.equal(mod(x[5:6]), y[5:6])

@@ -1,0 +1,86 @@
+"""Streaming (cached) mode on the GPU: block-by-block output equals the offline result with the fixed
+latency of SURVEY.md A.4, for the config-3 shape (many streams x block 2048) and for awkward block sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pqmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pq():
+    import pqmf_b200
+
+    return pqmf_b200
+
+
+def _run_stream(mod, x, block):
+    ys, outs = [], []
+    for i in range(0, x.shape[-1], block):
+        yb = mod.forward_stream(x[..., i : i + block].contiguous())
+        ys.append(yb)
+        outs.append(mod.inverse_stream(yb))
+    return torch.cat(ys, dim=-1), torch.cat(outs, dim=-1)
+
+
+@pytest.mark.parametrize("m,block,streams,exact", ((16, 2048, 7, False), (16, 2048, 7, True), (16, 512, 3, False), (16, 48, 2, False),
+                                                 (8, 256, 3, False), (64, 4096, 2, False), (16, 4096 + 32, 2, False)))
+def test_streamed_equals_offline(golden, pq, m, block, streams, exact):
+    hk = golden(f"bank_M{m}.npz")["hk"]
+    length = hk.shape[1]
+    k_taps = length // m
+    n_blocks = 5
+    t = n_blocks * block
+    x = O.audio_like((streams, 1, t), 99 + block)
+    mod = pq.CachedPQMF(100, m, exact=exact).cuda()
+    xd = torch.from_numpy(x).cuda()
+    y_s, out_s = _run_stream(mod, xd, block)
+    # invariant 1: stream_analysis(x) == offline_cached_forward(cat[zeros(L/2), x])[..., :T/M]
+    xz = torch.cat([torch.zeros(streams, 1, length // 2, device="cuda"), xd], dim=-1)
+    y_off = mod.forward(xz)[..., : t // m]
+    assert (y_s - y_off).abs().max().item() <= 2e-6
+    # invariant 2: stream_synthesis(s) == offline_cached_inverse(cat[zeros(K/2 frames), s])[..., :T]
+    sz = torch.cat([torch.zeros(streams, m, k_taps // 2, device="cuda"), y_s], dim=-1)
+    out_off = mod.inverse(sz)[..., :t]
+    assert (out_s - out_off).abs().max().item() <= 4e-6
+    # and both against the float64 oracle run as one long causal stream
+    st = O.StreamState(streams, m, length)
+    y64 = O.stream_analysis(x[:, 0], hk, st)
+    o64 = O.stream_synthesis(y_s.cpu().numpy(), hk, st)
+    assert np.abs(y_s.cpu().numpy() - y64).max() <= TOL / 2
+    assert np.abs(out_s.cpu().numpy()[:, 0] - o64).max() <= TOL / 2
+    # reconstruction after the fixed latency
+    lat = mod.cumulative_delay
+    assert lat == length // 2 + (k_taps // 2) * m + m
+    assert O.snr_db(x[..., : t - lat], out_s.cpu().numpy()[..., lat:]) > 30.0
+
+
+def test_streaming_flag_routes_forward_and_reset(golden, pq):
+    mod = pq.CachedPQMF(100, 16, streaming=True).cuda()
+    x = torch.from_numpy(O.audio_like((4, 1, 4096), 3)).cuda()
+    a = torch.cat([mod(x[..., :2048].contiguous()), mod(x[..., 2048:].contiguous())], dim=-1)
+    mod.reset_stream()
+    b = torch.cat([mod.forward_stream(x[..., :2048].contiguous()), mod.forward_stream(x[..., 2048:].contiguous())], dim=-1)
+    assert torch.equal(a, b)
+    mod.reset_stream()
+    c = mod(x[..., :2048].contiguous())
+    assert torch.equal(c, a[..., :128])
+
+
+def test_config3_many_streams(pq):
+    """BASELINE config 3 at reduced stream count for the parity check (4096 streams is the bench shape):
+    512 streams x block 2048 x 8 blocks, state carried across blocks."""
+    torch.manual_seed(1)
+    streams, block, n_blocks = 512, 2048, 8
+    mod = pq.CachedPQMF(100, 16).cuda()
+    x = (0.5 * torch.randn(streams, 1, block * n_blocks, device="cuda")).clamp_(-1, 1)
+    y_s, out_s = _run_stream(mod, x, block)
+    xz = torch.cat([torch.zeros(streams, 1, 256, device="cuda"), x], dim=-1)
+    assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 2e-6
+    lat = mod.cumulative_delay
+    err = out_s[..., lat:] - x[..., :-lat]
+    snr = 10 * torch.log10((x[..., :-lat] ** 2).sum() / (err ** 2).sum())
+    assert snr.item() > 30.0

@@ -1,0 +1,159 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/pqmf_b200.h declares, the
+module API mirrors the reference's (constructor, buffers, state_dict keys, errors, TorchScript), and nothing
+falls back to the CPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pq():
+    import pqmf_b200
+
+    return pqmf_b200
+
+
+def test_cabi_exports_every_declared_symbol(pq):
+    header = open(os.path.join(ROOT, "include", "pqmf_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pqmf_[a-z0-9_]+)\s*\(", header))
+    assert {"pqmf_analysis_f32", "pqmf_synthesis_f32", "pqmf_analysis_stream_f32", "pqmf_synthesis_stream_f32",
+            "pqmf_build_tables_f32", "pqmf_roundtrip_host_f32"} <= declared
+    lib = ctypes.CDLL(pq.library_paths()[0])
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pqmf_b200.h but not exported"
+    assert lib.pqmf_abi_version() == 1
+
+
+def test_torch_ops_are_registered_for_cuda_only(pq):
+    for op in ("analysis", "synthesis", "analysis_stream", "synthesis_stream"):
+        assert hasattr(torch.ops.pqmf_b200, op)
+    mod = pq.PQMF(100, 16)
+    with pytest.raises((RuntimeError, NotImplementedError)) as e:
+        mod(torch.zeros(1, 1, 64))
+    assert "CPU" in str(e.value)  # no CPU fallback: the dispatcher has no CPU kernel for the op
+
+
+def test_module_surface_matches_reference(pq, golden):
+    mod = pq.CachedPQMF(100, 16)
+    assert list(mod.state_dict().keys()) == ["hk", "h", "forward_conv.weight", "inverse_conv.weight"]
+    assert mod.n_band == 16 and mod.polyphase is True and mod.n_channels == 1
+    assert mod.hk.shape == (16, 512) and mod.h.shape == (377,)
+    assert mod.forward_conv.weight.shape == (16, 1, 513) and mod.forward_conv._pad == (256, 256)
+    assert mod.inverse_conv.weight.shape == (16, 16, 33) and mod.inverse_conv._pad == (16, 16)
+    mod.script_cache()
+    g = golden("ts_M16.npz")
+    assert np.array_equal(mod.h.numpy(), g["h"])
+    assert np.abs(mod.hk.numpy() - g["hk"]).max() <= 1e-8
+    assert np.abs(mod.inverse_conv.weight.detach().numpy() - g["inv_weight"]).max() <= 1e-8
+    with pytest.raises(AssertionError):
+        pq.PQMF(100, 12)
+    pq.PQMF(100, 12, polyphase=False)
+    ident = pq.PQMF(100, 16)
+    ident.n_band = 1
+    x = torch.zeros(1, 1, 8)
+    assert ident(x) is x and ident.inverse(x) is x  # n_band == 1 is the identity (reference pqmf.py:250, :280)
+
+
+@pytest.mark.parametrize("m", (2, 4, 8, 16, 32, 64))
+def test_design_matches_reference_banks(pq, golden, m):
+    g = golden(f"bank_M{m}.npz")
+    mod = pq.PQMF(100, m)
+    assert np.array_equal(mod.h.numpy(), g["h"])
+    assert np.abs(mod.hk.numpy() - g["hk"]).max() <= 1e-8
+
+
+def test_public_helper_names(pq):
+    for name in ("reverse_half", "get_prototype", "get_qmf_bank", "kaiser_filter", "loss_wc", "center_pad_next_pow_2", "make_odd",
+                 "polyphase_forward", "polyphase_inverse", "classic_forward", "classic_inverse", "PQMF", "CachedPQMF"):
+        assert hasattr(pq, name)
+    x = torch.arange(24.0).reshape(1, 4, 6)
+    r = pq.reverse_half(x)
+    assert torch.equal(r[0, 1, ::2], -x[0, 1, ::2]) and torch.equal(r[0, 1, 1::2], x[0, 1, 1::2]) and torch.equal(r[0, 0], x[0, 0])
+    assert pq.center_pad_next_pow_2(torch.ones(2, 377)).shape == (2, 512)
+    assert pq.make_odd(torch.ones(2, 512)).shape == (2, 513) and pq.make_odd(torch.ones(3)).shape == (3,)
+
+
+def test_state_dict_roundtrip_refreshes_tables(pq):
+    a = pq.CachedPQMF(100, 16)
+    b = pq.CachedPQMF(80, 16)
+    assert not torch.equal(a.h[:10], b.h[:10]) or a.h.shape != b.h.shape
+    sd = pq.CachedPQMF(100, 16).state_dict()
+    c = pq.CachedPQMF(100, 16)
+    c.load_state_dict(sd)
+    assert torch.equal(c.hk, a.hk)
+    assert c._tables.shape == a._tables.shape
+
+
+def test_torchscript_script_save_load(pq, tmp_path):
+    class Wrapper(torch.nn.Module):  # same shape as the reference's PQMFWrapper (PQMFWrapper.py:17-92)
+        def __init__(self):
+            super().__init__()
+            self.n_band = 16
+            self.pqmf = pq.CachedPQMF(100, 16)
+
+        @torch.jit.export
+        def forward(self, x: torch.Tensor) -> torch.Tensor:
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            return self.pqmf.forward(x)
+
+        @torch.jit.export
+        def inverse(self, x: torch.Tensor) -> torch.Tensor:
+            return self.pqmf.inverse(x)
+
+    scripted = torch.jit.script(Wrapper().eval())
+    path = str(tmp_path / "w.ts")
+    scripted.save(path)
+    loaded = torch.jit.load(path)
+    assert loaded.pqmf.hk.shape == (16, 512)
+    assert "pqmf_b200::analysis" in str(loaded.pqmf.forward.graph)
+    scripted_plain = torch.jit.script(pq.PQMF(100, 8))  # the reference's plain PQMF is not scriptable; ours is
+    assert "pqmf_b200::synthesis" in str(scripted_plain.inverse.graph)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not mounted")
+def test_reference_wrapper_scripts_unchanged_against_dropin(tmp_path):
+    """The reference's own PQMFWrapper.py, byte for byte, with dropin/ on sys.path instead of the reference's pqmf.py.
+    (Copied to a temp dir at test time only because the reference mount is read-only and the file mkdirs next to itself.)"""
+    import shutil
+
+    shutil.copy("/root/reference/PQMFWrapper.py", tmp_path / "PQMFWrapper.py")
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import torch, PQMFWrapper as W\n"
+        "import pqmf; assert 'pqmf_b200' in pqmf.CachedPQMF.__module__\n"
+        "w = W.PQMFWrapper(100, 16, 8192).eval()\n"
+        "s = torch.jit.script(w); s.save(%r)\n"
+        "l = torch.jit.load(%r)\n"
+        "assert l.get_methods() == ['forward', 'inverse', 'process']\n"
+        "print('OK', l.pqmf.hk.shape)\n"
+    ) % (str(tmp_path), os.path.join(ROOT, "dropin"), ROOT, str(tmp_path / "pqmf.ts"), str(tmp_path / "pqmf.ts"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_dropin_import_names():
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "from pqmf import CachedPQMF as A\n"
+            "from PQMF.pqmf import CachedPQMF as B, PQMF, reverse_half\n"
+            "assert A is B; print('OK')\n") % (os.path.join(ROOT, "dropin"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pseudo-quadrature-mirror-filter_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
