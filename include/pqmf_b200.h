@@ -42,6 +42,8 @@ extern "C" {
 #define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
                               * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
 
+#define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* from pqmf_build_tables_f32 */
+
 typedef void* pqmf_stream_t; /* cudaStream_t */
 
 int pqmf_abi_version(void);
@@ -56,10 +58,13 @@ int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
  * Factorises hk[k, r + 2M q] ~= g[r + 2M q] * C[k, r] from the fp32 prototype h
  * (buffer `h`, pqmf.py:231) and returns the largest |hk - g (x) C| in *residual (may be NULL).
  * tables_host must hold pqmf_tables_numel(M, L) floats: [ g (L) | C_hi (M*2M) | C_lo (M*2M) ].
+ * *fast_flags (may be NULL) receives the PQMF_FLAG_TAPS(...) bits describing which taps of g are pure zero
+ * padding; OR them into the `flags` of the compute calls that are given these tables (optional: without them
+ * the kernels run all L/2M taps).
  * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path. */
 long pqmf_tables_numel(int M, int L);
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
-                          double* residual);
+                          double* residual, unsigned* fast_flags);
 
 /* ---- offline analysis: PQMF.forward (pqmf.py:247-259 -> polyphase_forward :115-130 /
  *      classic_forward :160-177, then reverse_half) and CachedPQMF.forward (:339-343) ----

@@ -51,7 +51,8 @@ cabi.pqmf_path_for.argtypes = [ctypes.c_int, ctypes.c_int, _vp, ctypes.c_uint]
 cabi.pqmf_tables_numel.restype = ctypes.c_long
 cabi.pqmf_tables_numel.argtypes = [ctypes.c_int, ctypes.c_int]
 cabi.pqmf_build_tables_f32.restype = ctypes.c_int
-cabi.pqmf_build_tables_f32.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_double)]
+cabi.pqmf_build_tables_f32.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_uint)]
 cabi.pqmf_analysis_f32.restype = ctypes.c_int
 cabi.pqmf_analysis_f32.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_uint, _vp]
@@ -91,16 +92,17 @@ def library_paths():
 
 
 def build_tables(hk: torch.Tensor, h: torch.Tensor):
-    """Host-side factorisation hk ~= g (x) C for the fast path.  Returns (tables fp32 CPU tensor, residual);
-    an empty tensor when (n_band, L) has no fast path."""
+    """Host-side factorisation hk ~= g (x) C for the fast path.  Returns (tables fp32 CPU tensor, residual,
+    fast_flags); an empty tensor when (n_band, L) has no fast path."""
     m, length = int(hk.shape[0]), int(hk.shape[1])
     n = cabi.pqmf_tables_numel(m, length)
     if n <= 0:
-        return torch.zeros(0, dtype=torch.float32), float("nan")
+        return torch.zeros(0, dtype=torch.float32), float("nan"), 0
     hk_c = hk.detach().to("cpu", torch.float32).contiguous()
     h_c = h.detach().to("cpu", torch.float32).contiguous()
     out = torch.empty(n, dtype=torch.float32)
     res = ctypes.c_double(0.0)
+    fast_flags = ctypes.c_uint(0)
     check(cabi.pqmf_build_tables_f32(hk_c.data_ptr(), h_c.data_ptr(), int(h_c.numel()), m, length, out.data_ptr(),
-                                     ctypes.byref(res)), "pqmf_build_tables_f32")
-    return out, float(res.value)
+                                     ctypes.byref(res), ctypes.byref(fast_flags)), "pqmf_build_tables_f32")
+    return out, float(res.value), int(fast_flags.value)

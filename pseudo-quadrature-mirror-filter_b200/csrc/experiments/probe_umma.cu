@@ -130,7 +130,7 @@ int main() {
     for (auto& v : a) v = 0.1f * ((float)rand() / RAND_MAX - 0.5f);
     for (auto& v : b) v = 4.0f * ((float)rand() / RAND_MAX - 0.5f);
     std::vector<float> A(3 * 128 * K), B(3 * N * K);
-    for (int i = 0; i < 128 * K; ++i) { float hi = tf32_trunc(a[i]); float lo = a[i] - hi; A[i] = hi; A[128 * K + i] = lo; A[2 * 128 * K + i] = hi; }
+    for (int i = 0; i < 128 * K; ++i) { float hi = tf32_rn(a[i]); float lo = a[i] - hi; A[i] = hi; A[128 * K + i] = lo; A[2 * 128 * K + i] = hi; }
     for (int i = 0; i < N * K; ++i) { float hi = tf32_rn(b[i]); float lo = tf32_rn(b[i] - hi); B[i] = hi; B[N * K + i] = hi; B[2 * N * K + i] = lo; }
     std::vector<double> ref(128 * N, 0.0);
     for (int i = 0; i < 128; ++i) for (int j = 0; j < N; ++j) for (int k = 0; k < K; ++k) ref[i * N + j] += (double)a[i * K + k] * b[j * K + k];

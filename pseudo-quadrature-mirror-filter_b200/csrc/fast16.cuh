@@ -1,10 +1,329 @@
-// placeholder until the fold + tcgen05 kernels land
+// Fast path for n_band = 16, L = 512: window fold on CUDA cores (packed FFMA2) + cosine modulation on the
+// 5th-gen tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM), input tiles staged by the
+// TMA engine (cp.async.bulk + mbarrier), one fused pass per direction.
+//
+// Factorisation (reference arithmetic it replaces: pqmf.py:115-130 + :13-22 and :133-157):
+//   hk[k, r + 32 q] = g[r + 32 q] * C[k, r],   r in [0, 32), q in [0, 16)
+//   analysis : v[n, r] = sum_q g[r + 32 q] * X[16 n + r + 32 q - off]          (fold, 32 FMA / sample, exact fp32)
+//              y[k, n] = sigma(k, n) * sum_r C[k, r] * v[n, r]                 (modulation, [128 x 32] x [32 x 16] MMA)
+//   synthesis: w[n, r] = sum_k C[k, r] * sigma(k, n) * s[k, n]                 (modulation, [128 x 16] x [16 x 32] MMA)
+//              out[tau] = sum_{16 n + r + 32 q - off2 = tau} 16 g[r + 32 q] * w[n, r]   (overlap-add FIR)
+// Even / odd frames use disjoint 32-sample phase grids, so the fold is 32 phase sequences z_phi[i] = X[32 i + phi],
+// each run through two 16-tap FIRs.  Lanes own phase PAIRS (conflict-free LDS.64, natural float2 operands for
+// FFMA2), registers hold the taps and J = 8 outputs per parity.
+//
+// Taps: the prototype (N = 377 at attenuation 100) is centre-padded to 512, so g is identically zero for
+// q in {0, 1, 14, 15}; the <QLO = 2, QN = 12> instantiation skips them (25 % fewer FMAs, smaller halo).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
 namespace pqmf {
-inline bool fast16_supported(int M, int L) { (void)M; (void)L; return false; }
-inline bool fast16_analysis_ok(const float*, const float*, long, long) { return false; }
+
+constexpr int kF16Threads = 128;
+constexpr int kF16M = 16, kF16L = 512, kF16R = 32;  // bands, bank length, fold width 2M
+constexpr int kF16TileFrames = 128;                 // frames per tile = rows of one UMMA
+constexpr int kF16LboA = 2064;                      // bytes between K-chunks of an A plane (128*16 + 16 pad: conflict-free STS)
+constexpr int kF16Sbo = 128;                        // bytes between 8-row groups
+constexpr int kF16J = 8;                            // fold outputs per thread per frame parity
+
+inline bool fast16_supported(int M, int L) { return M == kF16M && L == kF16L; }
+
+struct F16Taps {
+  int qlo, qn;
+};
+// flags bits [8,12) = QLO, [12,17) = QN as produced by pqmf_build_tables_f32; anything else -> all 16 taps
+inline F16Taps fast16_taps_from_flags(unsigned flags) {
+  const int qlo = (flags >> 8) & 0xF, qn = (flags >> 12) & 0x1F;
+  if (qlo == 2 && qn == 12) return {2, 12};
+  return {0, 16};
+}
+inline unsigned fast16_flags_for_taps(int qlo, int qn) { return ((unsigned)qlo << 8) | ((unsigned)qn << 12); }
+
+// =============================================================================================
+// analysis
+// =============================================================================================
+struct F16AnalysisParams {
+  const float* x;        // [B, T]
+  const float* hist;     // [B, 512] or nullptr
+  float* y;              // [B, 16, F]
+  float* hist_out;       // [B, 512] or nullptr (streaming: last 512 samples of hist ++ x)
+  const float* tables;   // [ g (512) | C_hi (16*32) | C_lo (16*32) ]
+  long T, F;
+  int B;
+  int off;               // 256 offline, 512 streaming
+  int parity;            // global parity of frame 0
+  long tiles_per_row;
+  long n_tiles;
+};
+
+template <int QN>
+struct F16AnalysisSmem {
+  static constexpr int XS = 32 * (64 + QN);     // floats per x window
+  static constexpr int NXBUF = 2;
+  static constexpr int APLANE = 8 * kF16LboA;   // one tf32 plane of the A operand [128 x 32]
+  static constexpr int BPLANE = 8 * 256;        // one plane of B = C [16 x 32]: 8 K-chunks x (16 rows x 16 B)
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_A = OFF_X + NXBUF * XS * 4;
+  static constexpr int OFF_B = OFF_A + 2 * APLANE;
+  static constexpr int OFF_BAR = OFF_B + 2 * BPLANE;
+  static constexpr int BYTES = OFF_BAR + 64;
+};
+
+template <int QLO, int QN>
+__global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_kernel(F16AnalysisParams p) {
+  using S = F16AnalysisSmem<QN>;
+  constexpr int J = kF16J;
+  extern __shared__ __align__(128) unsigned char f16_smem[];
+  unsigned char* smem = f16_smem;
+  float* xs = reinterpret_cast<float*>(smem + S::OFF_X);
+  unsigned char* aplane = smem + S::OFF_A;
+  unsigned char* bplane = smem + S::OFF_B;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);  // [NXBUF]
+  uint64_t* mma_bar = xfull + S::NXBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pp = lane & 15;              // phase pair: phases 2pp, 2pp+1
+  const int mg = warp * 2 + (lane >> 4);  // m-group: frame pairs [8 mg, 8 mg + 8)
+  const int phi = 2 * pp;
+
+  // ---- one-time setup: barriers, TMEM, B operand (C hi/lo) in UMMA K-major layout, taps in registers ----
+  if (tid == 0) {
+    for (int i = 0; i < S::NXBUF; ++i) ptx::mbar_init(&xfull[i], 1);
+    ptx::mbar_init(mma_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, 32);
+    ptx::tmem_relinquish();
+  }
+  for (int e = tid; e < 2 * kF16M * kF16R; e += kF16Threads) {
+    const int pl = e / (kF16M * kF16R), rem = e % (kF16M * kF16R);
+    const int k = rem / kF16R, r = rem % kF16R;
+    *reinterpret_cast<float*>(bplane + pl * S::BPLANE + (r >> 2) * 256 + k * 16 + (r & 3) * 4) = __ldg(p.tables + kF16L + e);
+  }
+  float2 ge[QN], go[QN + 1];
+  {
+    const float* g = p.tables;
+#pragma unroll
+    for (int q = 0; q < QN; ++q) ge[q] = make_float2(__ldg(g + phi + 32 * (QLO + q)), __ldg(g + phi + 1 + 32 * (QLO + q)));
+    // odd frames: r = (phi + 16) mod 32; for phi < 16 the window starts one 32-sample row later (tap index shifts by one)
+    const int ro = (phi + 16) & 31;
+    const int shift = (pp < 8) ? 1 : 0;
+#pragma unroll
+    for (int q = 0; q <= QN; ++q) {
+      const int qq = q - shift;
+      go[q] = (qq >= 0 && qq < QN) ? make_float2(__ldg(g + ro + 32 * (QLO + qq)), __ldg(g + ro + 1 + 32 * (QLO + qq)))
+                                   : make_float2(0.f, 0.f);
+    }
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = ptx::umma_idesc_tf32(128, 16);
+
+  // ---- tile bookkeeping ----
+  auto tile_coords = [&](long tile, int& b, long& n0) {
+    b = (int)(tile / p.tiles_per_row);
+    n0 = (tile - (long)b * p.tiles_per_row) * kF16TileFrames;
+  };
+  // issue the TMA bulk copies of one tile's x window (thread 0) / zero the out-of-range part (all threads)
+  auto stage_tile = [&](long tile, int buf) {
+    int b;
+    long n0;
+    tile_coords(tile, b, n0);
+    const long s0 = n0 * 16 + 32 * QLO - p.off;  // first sample of the window, multiple of 16
+    float* dst = xs + buf * S::XS;
+    const long lo = max(s0, 0L), hi = min(s0 + S::XS, p.T);      // part inside x
+    const long hlo = max(s0, -512L), hhi = min(s0 + S::XS, 0L);  // part inside the history
+    const bool use_hist = p.hist != nullptr && hhi > hlo;
+    if (tid == 0) {
+      uint32_t bytes = 0;
+      if (hi > lo) bytes += (uint32_t)(hi - lo) * 4;
+      if (use_hist) bytes += (uint32_t)(hhi - hlo) * 4;
+      ptx::mbar_arrive_expect_tx(&xfull[buf], bytes);
+      if (hi > lo) ptx::bulk_g2s(dst + (lo - s0), p.x + (size_t)b * p.T + lo, (uint32_t)(hi - lo) * 4, &xfull[buf]);
+      if (use_hist) ptx::bulk_g2s(dst + (hlo - s0), p.hist + (size_t)b * 512 + (512 + hlo), (uint32_t)(hhi - hlo) * 4, &xfull[buf]);
+    }
+    if (s0 < 0 || s0 + S::XS > p.T) {  // edge tile: zero what no copy will write
+      for (int u = tid; u < S::XS; u += kF16Threads) {
+        const long s = s0 + u;
+        const bool from_x = s >= 0 && s < p.T;
+        const bool from_h = use_hist && s >= hlo && s < hhi;
+        if (!from_x && !from_h) dst[u] = 0.f;
+      }
+    }
+  };
+  // epilogue of one tile: D (TMEM) -> registers -> sign mask -> coalesced sub-band rows
+  auto epilogue = [&](long tile, int dbuf) {
+    int b;
+    long n0;
+    tile_coords(tile, b, n0);
+    uint32_t r[16];
+    ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dbuf * 16), r);
+    ptx::tmem_ld_wait();
+    const long n = n0 + tid;
+    if (n < p.F) {
+      const uint32_t flip = (((n + p.parity) & 1) == 0) ? 0x80000000u : 0u;
+      float* yp = p.y + (size_t)b * kF16M * p.F + n;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) __stcs(yp + (size_t)k * p.F, __uint_as_float(r[k] ^ ((k & 1) ? flip : 0u)));
+    }
+    // streaming: the CTA that owns the last tile of a row also rolls that row's history
+    if (p.hist_out != nullptr && n0 + kF16TileFrames >= p.F) {
+      const long c = p.T - 512 + tid * 4;  // position of this float4 in x (negative: still in the old history)
+      float4 v;
+      if (c >= 0) v = *reinterpret_cast<const float4*>(p.x + (size_t)b * p.T + c);
+      else v = *reinterpret_cast<const float4*>(p.hist + (size_t)b * 512 + (512 + c));
+      *reinterpret_cast<float4*>(p.hist_out + (size_t)b * 512 + tid * 4) = v;
+    }
+  };
+
+  const long first = blockIdx.x, stride = gridDim.x;
+  // prologue: stage the first NXBUF tiles
+  for (int i = 0; i < S::NXBUF; ++i) {
+    const long tile = first + (long)i * stride;
+    if (tile < p.n_tiles) stage_tile(tile, i);
+  }
+  __syncthreads();
+
+  long it = 0;
+  long prev_tile = -1;
+  for (long tile = first; tile < p.n_tiles; tile += stride, ++it) {
+    const int buf = (int)(it % S::NXBUF);
+    ptx::mbar_wait(&xfull[buf], (uint32_t)((it / S::NXBUF) & 1));
+
+    // ---------------- fold: 32 FMA / sample on packed fp32 ----------------
+    float2 ve[J], vo[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) ve[j] = vo[j] = make_float2(0.f, 0.f);
+    {
+      const float2* zp = reinterpret_cast<const float2*>(xs + buf * S::XS + 32 * (mg * J) + phi);
+#pragma unroll
+      for (int i = 0; i < J + QN; ++i) {
+        const float2 z = zp[16 * i];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int q = i - j;
+          if (q >= 0 && q < QN) ve[j] = ptx::ffma2(ge[q], z, ve[j]);
+          if (q >= 0 && q <= QN) vo[j] = ptx::ffma2(go[q], z, vo[j]);
+        }
+      }
+    }
+    // the previous tile's MMAs must have finished reading the A planes before they are overwritten
+    if (it > 0) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
+    // ---------------- split to tf32 hi + lo, store as the UMMA A operand ----------------
+    {
+      const int po = (pp + 8) & 15;  // chunk position of the odd-frame columns r = (phi + 16) mod 32
+      unsigned char* ae = aplane + (pp >> 1) * kF16LboA + (pp & 1) * 8;
+      unsigned char* ao = aplane + (po >> 1) * kF16LboA + (po & 1) * 8;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int row_e = 2 * (mg * J + j);
+        float2 hi, lo;
+        hi.x = __uint_as_float((__float_as_uint(ve[j].x) + 0x1000u) & 0xffffe000u);
+        hi.y = __uint_as_float((__float_as_uint(ve[j].y) + 0x1000u) & 0xffffe000u);
+        lo.x = ve[j].x - hi.x;
+        lo.y = ve[j].y - hi.y;
+        *reinterpret_cast<float2*>(ae + row_e * 16) = hi;
+        *reinterpret_cast<float2*>(ae + row_e * 16 + S::APLANE) = lo;
+        hi.x = __uint_as_float((__float_as_uint(vo[j].x) + 0x1000u) & 0xffffe000u);
+        hi.y = __uint_as_float((__float_as_uint(vo[j].y) + 0x1000u) & 0xffffe000u);
+        lo.x = vo[j].x - hi.x;
+        lo.y = vo[j].y - hi.y;
+        *reinterpret_cast<float2*>(ao + (row_e + 1) * 16) = hi;
+        *reinterpret_cast<float2*>(ao + (row_e + 1) * 16 + S::APLANE) = lo;
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    // x buffer `buf` is free again: stage the tile NXBUF iterations ahead
+    {
+      const long next = tile + (long)S::NXBUF * stride;
+      if (next < p.n_tiles) stage_tile(next, buf);
+    }
+    // ---------------- modulation: D[128 x 16] = A_hi B_hi + A_lo B_hi + A_hi B_lo ----------------
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t d = tmem + (uint32_t)((it & 1) * 16);
+      const uint32_t a_hi = ptx::smem_u32(aplane), a_lo = a_hi + S::APLANE;
+      const uint32_t b_hi = ptx::smem_u32(bplane), b_lo = b_hi + S::BPLANE;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t a = (term == 1) ? a_lo : a_hi;
+        const uint32_t bb = (term == 2) ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_tf32(d, ptx::umma_desc(a + ks * 2 * kF16LboA, kF16LboA, kF16Sbo), ptx::umma_desc(bb + ks * 2 * 256, 256, kF16Sbo),
+                         idesc, (term | ks) != 0);
+      }
+      ptx::umma_commit(mma_bar);
+    }
+    // ---------------- epilogue of the PREVIOUS tile overlaps this tile's MMAs ----------------
+    if (it > 0) {
+      ptx::tc_fence_after();
+      epilogue(prev_tile, (int)((it - 1) & 1));
+    }
+    prev_tile = tile;
+  }
+  if (it > 0) {
+    ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
+    ptx::tc_fence_after();
+    epilogue(prev_tile, (int)((it - 1) & 1));
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 32);
+}
+
+inline bool fast16_analysis_ok(const float* x, const float* y, long T, long F) {
+  return (T % 16) == 0 && F == T / 16 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 4) == 0 && T > 0;
+}
+
+template <int QLO, int QN>
+int f16_launch_analysis(const F16AnalysisParams& p, cudaStream_t st) {
+  using S = F16AnalysisSmem<QN>;
+  auto kern = f16_analysis_kernel<QLO, QN>;
+  static int sm_count = 0, ctas_per_sm = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kF16Threads, S::BYTES);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  long grid = (long)sm_count * ctas_per_sm;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, kF16Threads, S::BYTES, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// x [B,T] (+ hist [B,512]) -> y [B,16,F] (+ hist_out).  flags carry the tap window chosen by pqmf_build_tables_f32.
+inline int fast16_analysis(const float* x, const float* hist, float* y, float* hist_out, const float* tables, int B, long T, long F,
+                           int off, int parity, unsigned flags, cudaStream_t st) {
+  F16AnalysisParams p{};
+  p.x = x; p.hist = hist; p.y = y; p.hist_out = hist_out; p.tables = tables;
+  p.T = T; p.F = F; p.B = B; p.off = off; p.parity = parity & 1;
+  p.tiles_per_row = (F + kF16TileFrames - 1) / kF16TileFrames;
+  p.n_tiles = p.tiles_per_row * B;
+  if (hist != nullptr && ((uintptr_t)hist % 16 || (uintptr_t)hist_out % 16)) return -2;
+  const F16Taps t = fast16_taps_from_flags(flags);
+  if (t.qn == 12) return f16_launch_analysis<2, 12>(p, st);
+  return f16_launch_analysis<0, 16>(p, st);
+}
+
+// synthesis fast path: not built yet -> callers fall back to the direct form
 inline bool fast16_synthesis_ok(const float*, const float*, long) { return false; }
-inline int fast16_analysis(const float*, const float*, float*, float*, const float*, int, long, long, int, int, cudaStream_t) { return -2; }
-inline int fast16_synthesis(const float*, const float*, float*, float*, const float*, int, long, int, int, cudaStream_t) { return -2; }
+inline int fast16_synthesis(const float*, const float*, float*, float*, const float*, int, long, int, int, unsigned, cudaStream_t) {
+  return -2;
+}
+
 }  // namespace pqmf

@@ -142,7 +142,7 @@ int pqmf_path_for(int M, int L, const float* tables, unsigned flags) { return us
 long pqmf_tables_numel(int M, int L) { return pqmf::fast16_supported(M, L) ? (long)L + 2L * M * 2 * M : 0; }
 
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
-                          double* residual) {
+                          double* residual, unsigned* fast_flags) {
   if (!hk_host || !h_host || !tables_host || N <= 0 || N > L) return PQMF_ERR_ARG;
   if (!pqmf::fast16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
   // hk[k, r + 2M q] = (-1)^q * 2 hpad[r + 2M q] * cos((2k+1) pi/(2M) (r - c0) + (-1)^k pi/4)   
@@ -184,6 +184,13 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
       res = std::fmax(res, std::fabs((double)hk_host[(size_t)k * L + j] - model));
     }
   if (residual) *residual = res;
+  if (fast_flags) {
+    // taps q in {0,1,14,15} of every 32-sample phase are pure padding when the prototype is short enough
+    bool trimmed = true;
+    for (int j = 0; j < L; ++j)
+      if ((j < 64 || j >= 448) && g[j] != 0.f) trimmed = false;
+    *fast_flags = trimmed ? pqmf::fast16_flags_for_taps(2, 12) : pqmf::fast16_flags_for_taps(0, 16);
+  }
   return PQMF_OK;
 }
 
@@ -194,7 +201,7 @@ int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* ta
   if (!x || !y || !hk) return PQMF_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (use_fast(M, L, tables, flags) && pqmf::fast16_analysis_ok(x, y, T, n_frames)) {
-    int e = pqmf::fast16_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, st);
+    int e = pqmf::fast16_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   return analysis_direct(x, nullptr, y, hk, B, T, n_frames, M, L, L / 2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
@@ -208,7 +215,7 @@ int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const int off2 = L / 2 - delay_frames * M;
   if (use_fast(M, L, tables, flags) && pqmf::fast16_synthesis_ok(s, out, n_frames)) {
-    int e = pqmf::fast16_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, st);
+    int e = pqmf::fast16_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   return synthesis_direct(s, nullptr, out, hk, B, n_frames, M, L, off2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
@@ -225,7 +232,7 @@ int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const long F = T / M;
   if (use_fast(M, L, tables, flags) && pqmf::fast16_analysis_ok(x, y, T, F)) {
-    int e = pqmf::fast16_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, st);
+    int e = pqmf::fast16_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   int e = analysis_direct(x, state_in, y, hk, B, T, F, M, L, L, frame_parity, 0, st);
@@ -244,7 +251,7 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
   const int K = L / M;
   // history frames sit K frames before frame 0 of the block: their parity offset is (frame_parity - K)
   if (use_fast(M, L, tables, flags) && pqmf::fast16_synthesis_ok(s, out, n_frames)) {
-    int e = pqmf::fast16_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, st);
+    int e = pqmf::fast16_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   int e = synthesis_direct(s, state_in, out, hk, B, n_frames, M, L, -M, frame_parity, 0, st);

@@ -114,10 +114,11 @@ class PQMF(nn.Module):
     @torch.jit.unused
     def refresh_tables(self) -> None:
         """(Re)derive the fast-path coefficient tables from the current ``hk`` / ``h`` buffers."""
-        tables, residual = _lib.build_tables(self.hk, self.h)
+        tables, residual, fast_flags = _lib.build_tables(self.hk, self.h)
         if tables.numel() and not (residual <= _FOLD_RESIDUAL_LIMIT):
-            tables = torch.zeros(0)  # bank is not window x cosine: stay on the direct form
+            tables, fast_flags = torch.zeros(0), 0  # bank is not window x cosine: stay on the direct form
         self.fold_residual = residual
+        self._flags = (self._flags & 0xFF) | fast_flags
         self._tables = tables.to(self.hk.device)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
