@@ -127,16 +127,20 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
   const uint32_t tmem = *tmem_slot;
   const uint32_t idesc = ptx::umma_idesc_tf32(128, 16);
 
-  // ---- tile bookkeeping ----
-  auto tile_coords = [&](long tile, int& b, long& n0) {
-    b = (int)(tile / p.tiles_per_row);
-    n0 = (tile - (long)b * p.tiles_per_row) * kF16TileFrames;
+  // ---- tile bookkeeping: tile = first + it * stride walked incrementally as (row b, tile-in-row c), no divisions ----
+  const unsigned tpr = (unsigned)p.tiles_per_row;
+  const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
+  auto advance = [&](unsigned& b, unsigned& c) {
+    b += step_b;
+    c += step_c;
+    if (c >= tpr) {
+      c -= tpr;
+      ++b;
+    }
   };
   // issue the TMA bulk copies of one tile's x window (thread 0) / zero the out-of-range part (all threads)
-  auto stage_tile = [&](long tile, int buf) {
-    int b;
-    long n0;
-    tile_coords(tile, b, n0);
+  auto stage_tile = [&](unsigned b, unsigned c, int buf) {
+    const long n0 = (long)c * kF16TileFrames;
     const long s0 = n0 * 16 + 32 * QLO - p.off;  // first sample of the window, multiple of 16
     float* dst = xs + buf * S::XS;
     const long lo = max(s0, 0L), hi = min(s0 + S::XS, p.T);      // part inside x
@@ -160,10 +164,8 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
     }
   };
   // epilogue of one tile: D (TMEM) -> registers -> sign mask -> coalesced sub-band rows
-  auto epilogue = [&](long tile, int dbuf) {
-    int b;
-    long n0;
-    tile_coords(tile, b, n0);
+  auto epilogue = [&](unsigned b, unsigned c, int dbuf) {
+    const long n0 = (long)c * kF16TileFrames;
     uint32_t r[16];
     ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dbuf * 16), r);
     ptx::tmem_ld_wait();
@@ -185,15 +187,18 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
   };
 
   const long first = blockIdx.x, stride = gridDim.x;
+  unsigned cur_b = blockIdx.x / tpr, cur_c = blockIdx.x % tpr;  // tile being folded
+  unsigned nxt_b = cur_b, nxt_c = cur_c;                        // tile being staged (NXBUF iterations ahead)
   // prologue: stage the first NXBUF tiles
   for (int i = 0; i < S::NXBUF; ++i) {
     const long tile = first + (long)i * stride;
-    if (tile < p.n_tiles) stage_tile(tile, i);
+    if (tile < p.n_tiles) stage_tile(nxt_b, nxt_c, i);
+    advance(nxt_b, nxt_c);
   }
   __syncthreads();
 
   long it = 0;
-  long prev_tile = -1;
+  unsigned prev_b = 0, prev_c = 0;
   for (long tile = first; tile < p.n_tiles; tile += stride, ++it) {
     const int buf = (int)(it % S::NXBUF);
     ptx::mbar_wait(&xfull[buf], (uint32_t)((it / S::NXBUF) & 1));
@@ -246,7 +251,8 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
     // x buffer `buf` is free again: stage the tile NXBUF iterations ahead
     {
       const long next = tile + (long)S::NXBUF * stride;
-      if (next < p.n_tiles) stage_tile(next, buf);
+      if (next < p.n_tiles) stage_tile(nxt_b, nxt_c, buf);
+      advance(nxt_b, nxt_c);
     }
     // ---------------- modulation: D[128 x 16] = A_hi B_hi + A_lo B_hi + A_hi B_lo ----------------
     if (tid == 0) {
@@ -268,14 +274,16 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
     // ---------------- epilogue of the PREVIOUS tile overlaps this tile's MMAs ----------------
     if (it > 0) {
       ptx::tc_fence_after();
-      epilogue(prev_tile, (int)((it - 1) & 1));
+      epilogue(prev_b, prev_c, (int)((it - 1) & 1));
     }
-    prev_tile = tile;
+    prev_b = cur_b;
+    prev_c = cur_c;
+    advance(cur_b, cur_c);
   }
   if (it > 0) {
     ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
     ptx::tc_fence_after();
-    epilogue(prev_tile, (int)((it - 1) & 1));
+    epilogue(prev_b, prev_c, (int)((it - 1) & 1));
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -290,17 +298,20 @@ template <int QLO, int QN>
 int f16_launch_analysis(const F16AnalysisParams& p, cudaStream_t st) {
   using S = F16AnalysisSmem<QN>;
   auto kern = f16_analysis_kernel<QLO, QN>;
-  static int sm_count = 0, ctas_per_sm = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  constexpr int kCtasPerSm = (QN <= 12) ? 4 : 3;  // matches __launch_bounds__ and the shared-memory footprint
+  static int sm_count[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (sm_count[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
     if (e != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kF16Threads, S::BYTES);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    sm_count[dev] = n > 0 ? n : 148;
   }
-  long grid = (long)sm_count * ctas_per_sm;
+  if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
+  long grid = (long)sm_count[dev] * kCtasPerSm;
   if (grid > p.n_tiles) grid = p.n_tiles;
   kern<<<(unsigned)grid, kF16Threads, S::BYTES, st>>>(p);
   return (int)cudaGetLastError();
