@@ -331,10 +331,4 @@ inline int fast16_analysis(const float* x, const float* hist, float* y, float* h
   return f16_launch_analysis<0, 16>(p, st);
 }
 
-// synthesis fast path: not built yet -> callers fall back to the direct form
-inline bool fast16_synthesis_ok(const float*, const float*, long) { return false; }
-inline int fast16_synthesis(const float*, const float*, float*, float*, const float*, int, long, int, int, unsigned, cudaStream_t) {
-  return -2;
-}
-
 }  // namespace pqmf

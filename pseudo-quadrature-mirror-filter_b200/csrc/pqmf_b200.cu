@@ -13,6 +13,7 @@
 
 #include "direct_form.cuh"
 #include "fast16.cuh"
+#include "fast16_synth.cuh"
 
 namespace {
 
