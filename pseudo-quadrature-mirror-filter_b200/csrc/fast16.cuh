@@ -1,6 +1,6 @@
 // Fast path for n_band = 16, L = 512: window fold on CUDA cores (packed FFMA2) + cosine modulation on the
-// 5th-gen tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM), input tiles staged by the
-// TMA engine (cp.async.bulk + mbarrier), one fused pass per direction.
+// 5th-gen tensor cores (tcgen05.mma kind::f16 on a two-term fp16 split, fp32 accumulators in TMEM), input tiles
+// staged by the TMA engine (cp.async.bulk + mbarrier), one fused pass per direction.
 //
 // Factorisation (reference arithmetic it replaces: pqmf.py:115-130 + :13-22 and :133-157):
 //   hk[k, r + 32 q] = g[r + 32 q] * C[k, r],   r in [0, 32), q in [0, 16)
@@ -12,9 +12,16 @@
 // each run through two 16-tap FIRs.  Lanes own phase PAIRS (conflict-free LDS.64, natural float2 operands for
 // FFMA2), registers hold the taps and J = 8 outputs per parity.
 //
+// Modulation precision: v = h1 + 2^-11 h2 and C = c1 + c2 with all four terms fp16; the MMAs compute
+//   h1 [c1 | c2]  (one N = 32 instruction stream: columns 0-15 main term, 16-31 the c2 correction)  +  h2 (2^-11 c1)
+// with exact fp16 x fp16 products accumulated in fp32, dropping only h2 c2 ~ 2^-23 |v C|: fp32-level accuracy for
+// 12 bytes/sample of shared-memory operand traffic (a 3xTF32 split costs 24; this kernel is shared-memory-bandwidth
+// bound).
+//
 // Taps: the prototype (N = 377 at attenuation 100) is centre-padded to 512, so g is identically zero for
 // q in {0, 1, 14, 15}; the <QLO = 2, QN = 12> instantiation skips them (25 % fewer FMAs, smaller halo).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,9 +32,12 @@ namespace pqmf {
 constexpr int kF16Threads = 128;
 constexpr int kF16M = 16, kF16L = 512, kF16R = 32;  // bands, bank length, fold width 2M
 constexpr int kF16TileFrames = 128;                 // frames per tile = rows of one UMMA
-constexpr int kF16LboA = 2064;                      // bytes between K-chunks of an A plane (128*16 + 16 pad: conflict-free STS)
-constexpr int kF16Sbo = 128;                        // bytes between 8-row groups
 constexpr int kF16J = 8;                            // fold outputs per thread per frame parity
+// A operand planes [128 rows x 32 K] fp16, K-major no-swizzle: 4 K-chunks of 8 halves; rows of a core matrix 16 B apart,
+// 8-row groups SBO apart, chunks LBO apart.  SBO = 160 and LBO = 16*160 + 16 make the split's STS.32 conflict-free:
+// bank = 4*chunk + (pair & 3) + 16*(m-group & 1).
+constexpr int kF16SboA = 160;
+constexpr int kF16LboA = 16 * kF16SboA + 16;
 
 inline bool fast16_supported(int M, int L) { return M == kF16M && L == kF16L; }
 
@@ -42,6 +52,11 @@ inline F16Taps fast16_taps_from_flags(unsigned flags) {
 }
 inline unsigned fast16_flags_for_taps(int qlo, int qn) { return ((unsigned)qlo << 8) | ((unsigned)qn << 12); }
 
+__device__ __forceinline__ uint16_t f16_bits(float v) {
+  const __half h = __float2half_rn(v);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+
 // =============================================================================================
 // analysis
 // =============================================================================================
@@ -50,7 +65,7 @@ struct F16AnalysisParams {
   const float* hist;     // [B, 512] or nullptr
   float* y;              // [B, 16, F]
   float* hist_out;       // [B, 512] or nullptr (streaming: last 512 samples of hist ++ x)
-  const float* tables;   // [ g (512) | C_hi (16*32) | C_lo (16*32) ]
+  const float* tables;   // [ g (512) | c1 (16*32) | c2 (16*32) ],  C = c1 + c2, both fp16-representable
   long T, F;
   int B;
   int off;               // 256 offline, 512 streaming
@@ -63,26 +78,37 @@ template <int QN>
 struct F16AnalysisSmem {
   static constexpr int XS = 32 * (64 + QN);     // floats per x window
   static constexpr int NXBUF = 2;
-  static constexpr int APLANE = 8 * kF16LboA;   // one tf32 plane of the A operand [128 x 32]
-  static constexpr int BPLANE = 8 * 256;        // one plane of B = C [16 x 32]: 8 K-chunks x (16 rows x 16 B)
+  static constexpr int APLANE = 4 * kF16LboA;   // one fp16 plane of the A operand [128 x 32]
+  static constexpr int BCAT = 4 * 512;          // B = [c1 | c2]: N = 32 rows x K = 32 fp16, 4 K-chunks x (32 rows x 16 B)
+  static constexpr int BRES = 4 * 256;          // B = 2^-11 c1 : N = 16 rows x K = 32 fp16
   static constexpr int OFF_X = 0;
   static constexpr int OFF_A = OFF_X + NXBUF * XS * 4;
   static constexpr int OFF_B = OFF_A + 2 * APLANE;
-  static constexpr int OFF_BAR = OFF_B + 2 * BPLANE;
+  static constexpr int OFF_BAR = OFF_B + BCAT + BRES;
   static constexpr int BYTES = OFF_BAR + 64;
 };
 
+// Synchronisation is mbarrier-only inside the tile loop (no __syncthreads): warps drift freely and only meet where
+// data really flows.
+//   xfull[b]  (tx)        TMA -> fold        : x window b has landed
+//   xempty[b] (4 warps)   fold -> TMA issuer : all four warps are done reading window b
+//   afull     (128 thr)   split -> MMA issuer: the A planes of this tile are complete (and D of tile t-1 was drained)
+//   mma_bar   (commit)    MMA -> everyone    : tile's MMAs retired: A planes reusable, D readable
+// Warp 0 doubles as TMA issuer + MMA issuer (one elected lane); it is the only warp that ever waits on other warps.
 template <int QLO, int QN>
-__global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_kernel(F16AnalysisParams p) {
+__global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16AnalysisParams p) {
   using S = F16AnalysisSmem<QN>;
   constexpr int J = kF16J;
   extern __shared__ __align__(128) unsigned char f16_smem[];
   unsigned char* smem = f16_smem;
   float* xs = reinterpret_cast<float*>(smem + S::OFF_X);
   unsigned char* aplane = smem + S::OFF_A;
-  unsigned char* bplane = smem + S::OFF_B;
+  unsigned char* bcat = smem + S::OFF_B;
+  unsigned char* bres = bcat + S::BCAT;
   uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);  // [NXBUF]
-  uint64_t* mma_bar = xfull + S::NXBUF;
+  uint64_t* xempty = xfull + S::NXBUF;                                // [NXBUF]
+  uint64_t* afull = xempty + S::NXBUF;
+  uint64_t* mma_bar = afull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,20 +116,27 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
   const int mg = warp * 2 + (lane >> 4);  // m-group: frame pairs [8 mg, 8 mg + 8)
   const int phi = 2 * pp;
 
-  // ---- one-time setup: barriers, TMEM, B operand (C hi/lo) in UMMA K-major layout, taps in registers ----
+  // ---- one-time setup: barriers, TMEM, B operands in UMMA K-major layout, taps in registers ----
   if (tid == 0) {
-    for (int i = 0; i < S::NXBUF; ++i) ptx::mbar_init(&xfull[i], 1);
+    for (int i = 0; i < S::NXBUF; ++i) {
+      ptx::mbar_init(&xfull[i], 1);
+      ptx::mbar_init(&xempty[i], kF16Threads / 32);
+    }
+    ptx::mbar_init(afull, kF16Threads);
     ptx::mbar_init(mma_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_slot, 32);
+    ptx::tmem_alloc(tmem_slot, 64);
     ptx::tmem_relinquish();
   }
   for (int e = tid; e < 2 * kF16M * kF16R; e += kF16Threads) {
     const int pl = e / (kF16M * kF16R), rem = e % (kF16M * kF16R);
     const int k = rem / kF16R, r = rem % kF16R;
-    *reinterpret_cast<float*>(bplane + pl * S::BPLANE + (r >> 2) * 256 + k * 16 + (r & 3) * 4) = __ldg(p.tables + kF16L + e);
+    const float c = __ldg(p.tables + kF16L + e);
+    const int n = pl * 16 + k;  // row of [c1 | c2]
+    *reinterpret_cast<uint16_t*>(bcat + (r >> 3) * 512 + n * 16 + (r & 7) * 2) = f16_bits(c);
+    if (pl == 0) *reinterpret_cast<uint16_t*>(bres + (r >> 3) * 256 + k * 16 + (r & 7) * 2) = f16_bits(c * (1.f / 2048.f));
   }
   float2 ge[QN], go[QN + 1];
   {
@@ -125,7 +158,6 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = ptx::umma_idesc_tf32(128, 16);
 
   // ---- tile bookkeeping: tile = first + it * stride walked incrementally as (row b, tile-in-row c), no divisions ----
   const unsigned tpr = (unsigned)p.tiles_per_row;
@@ -138,7 +170,8 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
       ++b;
     }
   };
-  // issue the TMA bulk copies of one tile's x window (thread 0) / zero the out-of-range part (all threads)
+  // WARP 0 ONLY: zero the out-of-range part of an edge window (all lanes), then one lane arms the barrier and
+  // issues the TMA bulk copies.  The arrive releases the zero fill to the waiting warps.
   auto stage_tile = [&](unsigned b, unsigned c, int buf) {
     const long n0 = (long)c * kF16TileFrames;
     const long s0 = n0 * 16 + 32 * QLO - p.off;  // first sample of the window, multiple of 16
@@ -146,7 +179,16 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
     const long lo = max(s0, 0L), hi = min(s0 + S::XS, p.T);      // part inside x
     const long hlo = max(s0, -512L), hhi = min(s0 + S::XS, 0L);  // part inside the history
     const bool use_hist = p.hist != nullptr && hhi > hlo;
-    if (tid == 0) {
+    if (s0 < 0 || s0 + S::XS > p.T) {
+      for (int u = lane; u < S::XS; u += 32) {
+        const long s = s0 + u;
+        const bool from_x = s >= 0 && s < p.T;
+        const bool from_h = use_hist && s >= hlo && s < hhi;
+        if (!from_x && !from_h) dst[u] = 0.f;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
       uint32_t bytes = 0;
       if (hi > lo) bytes += (uint32_t)(hi - lo) * 4;
       if (use_hist) bytes += (uint32_t)(hhi - hlo) * 4;
@@ -154,34 +196,29 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
       if (hi > lo) ptx::bulk_g2s(dst + (lo - s0), p.x + (size_t)b * p.T + lo, (uint32_t)(hi - lo) * 4, &xfull[buf]);
       if (use_hist) ptx::bulk_g2s(dst + (hlo - s0), p.hist + (size_t)b * 512 + (512 + hlo), (uint32_t)(hhi - hlo) * 4, &xfull[buf]);
     }
-    if (s0 < 0 || s0 + S::XS > p.T) {  // edge tile: zero what no copy will write
-      for (int u = tid; u < S::XS; u += kF16Threads) {
-        const long s = s0 + u;
-        const bool from_x = s >= 0 && s < p.T;
-        const bool from_h = use_hist && s >= hlo && s < hhi;
-        if (!from_x && !from_h) dst[u] = 0.f;
-      }
-    }
   };
-  // epilogue of one tile: D (TMEM) -> registers -> sign mask -> coalesced sub-band rows
+  // epilogue of one tile: D (TMEM) -> registers -> main + correction columns -> sign mask -> coalesced sub-band rows
   auto epilogue = [&](unsigned b, unsigned c, int dbuf) {
     const long n0 = (long)c * kF16TileFrames;
-    uint32_t r[16];
-    ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dbuf * 16), r);
+    uint32_t r[32];
+    ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dbuf * 32), r);
     ptx::tmem_ld_wait();
     const long n = n0 + tid;
     if (n < p.F) {
       const uint32_t flip = (((n + p.parity) & 1) == 0) ? 0x80000000u : 0u;
       float* yp = p.y + (size_t)b * kF16M * p.F + n;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) __stcs(yp + (size_t)k * p.F, __uint_as_float(r[k] ^ ((k & 1) ? flip : 0u)));
+      for (int k = 0; k < 16; ++k) {
+        const float v = __uint_as_float(r[k]) + __uint_as_float(r[16 + k]);
+        __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
+      }
     }
     // streaming: the CTA that owns the last tile of a row also rolls that row's history
     if (p.hist_out != nullptr && n0 + kF16TileFrames >= p.F) {
-      const long c = p.T - 512 + tid * 4;  // position of this float4 in x (negative: still in the old history)
+      const long cpos = p.T - 512 + tid * 4;  // position of this float4 in x (negative: still in the old history)
       float4 v;
-      if (c >= 0) v = *reinterpret_cast<const float4*>(p.x + (size_t)b * p.T + c);
-      else v = *reinterpret_cast<const float4*>(p.hist + (size_t)b * 512 + (512 + c));
+      if (cpos >= 0) v = *reinterpret_cast<const float4*>(p.x + (size_t)b * p.T + cpos);
+      else v = *reinterpret_cast<const float4*>(p.hist + (size_t)b * 512 + (512 + cpos));
       *reinterpret_cast<float4*>(p.hist_out + (size_t)b * 512 + tid * 4) = v;
     }
   };
@@ -189,19 +226,19 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
   const long first = blockIdx.x, stride = gridDim.x;
   unsigned cur_b = blockIdx.x / tpr, cur_c = blockIdx.x % tpr;  // tile being folded
   unsigned nxt_b = cur_b, nxt_c = cur_c;                        // tile being staged (NXBUF iterations ahead)
-  // prologue: stage the first NXBUF tiles
-  for (int i = 0; i < S::NXBUF; ++i) {
-    const long tile = first + (long)i * stride;
-    if (tile < p.n_tiles) stage_tile(nxt_b, nxt_c, i);
-    advance(nxt_b, nxt_c);
+  if (warp == 0) {  // prologue: stage the first NXBUF tiles
+    for (int i = 0; i < S::NXBUF; ++i) {
+      const long tile = first + (long)i * stride;
+      if (tile < p.n_tiles) stage_tile(nxt_b, nxt_c, i);
+      advance(nxt_b, nxt_c);
+    }
   }
-  __syncthreads();
 
   long it = 0;
   unsigned prev_b = 0, prev_c = 0;
   for (long tile = first; tile < p.n_tiles; tile += stride, ++it) {
-    const int buf = (int)(it % S::NXBUF);
-    ptx::mbar_wait(&xfull[buf], (uint32_t)((it / S::NXBUF) & 1));
+    const int buf = (int)(it & 1);
+    ptx::mbar_wait(&xfull[buf], (uint32_t)((it >> 1) & 1));
 
     // ---------------- fold: 32 FMA / sample on packed fp32 ----------------
     float2 ve[J], vo[J];
@@ -220,56 +257,58 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&xempty[buf]);  // this warp no longer reads x window `buf`
     // the previous tile's MMAs must have finished reading the A planes before they are overwritten
     if (it > 0) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
-    // ---------------- split to tf32 hi + lo, store as the UMMA A operand ----------------
+    // ---------------- two-term fp16 split, stored as the UMMA A operand (h1 plane, h2 plane) ----------------
     {
-      const int po = (pp + 8) & 15;  // chunk position of the odd-frame columns r = (phi + 16) mod 32
-      unsigned char* ae = aplane + (pp >> 1) * kF16LboA + (pp & 1) * 8;
-      unsigned char* ao = aplane + (po >> 1) * kF16LboA + (po & 1) * 8;
+      const int po = (pp + 8) & 15;  // K position of the odd-frame columns r = (phi + 16) mod 32
+      unsigned char* ae = aplane + (pp >> 2) * kF16LboA + (pp & 3) * 4 + (2 * mg) * kF16SboA;
+      unsigned char* ao = aplane + (po >> 2) * kF16LboA + (po & 3) * 4 + (2 * mg) * kF16SboA;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const int row_e = 2 * (mg * J + j);
-        float2 hi, lo;
-        hi.x = __uint_as_float((__float_as_uint(ve[j].x) + 0x1000u) & 0xffffe000u);
-        hi.y = __uint_as_float((__float_as_uint(ve[j].y) + 0x1000u) & 0xffffe000u);
-        lo.x = ve[j].x - hi.x;
-        lo.y = ve[j].y - hi.y;
-        *reinterpret_cast<float2*>(ae + row_e * 16) = hi;
-        *reinterpret_cast<float2*>(ae + row_e * 16 + S::APLANE) = lo;
-        hi.x = __uint_as_float((__float_as_uint(vo[j].x) + 0x1000u) & 0xffffe000u);
-        hi.y = __uint_as_float((__float_as_uint(vo[j].y) + 0x1000u) & 0xffffe000u);
-        lo.x = vo[j].x - hi.x;
-        lo.y = vo[j].y - hi.y;
-        *reinterpret_cast<float2*>(ao + (row_e + 1) * 16) = hi;
-        *reinterpret_cast<float2*>(ao + (row_e + 1) * 16 + S::APLANE) = lo;
+        const int re = 2 * j, rd = 2 * j + 1;  // row within this m-group's 16 rows (even frame, odd frame)
+        uint32_t h1, h2;
+        ptx::split_f16x2(ve[j], h1, h2);
+        *reinterpret_cast<uint32_t*>(ae + (re >> 3) * kF16SboA + (re & 7) * 16) = h1;
+        *reinterpret_cast<uint32_t*>(ae + (re >> 3) * kF16SboA + (re & 7) * 16 + S::APLANE) = h2;
+        ptx::split_f16x2(vo[j], h1, h2);
+        *reinterpret_cast<uint32_t*>(ao + (rd >> 3) * kF16SboA + (rd & 7) * 16) = h1;
+        *reinterpret_cast<uint32_t*>(ao + (rd >> 3) * kF16SboA + (rd & 7) * 16 + S::APLANE) = h2;
       }
     }
     ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
-    // x buffer `buf` is free again: stage the tile NXBUF iterations ahead
-    {
-      const long next = tile + (long)S::NXBUF * stride;
-      if (next < p.n_tiles) stage_tile(nxt_b, nxt_c, buf);
-      advance(nxt_b, nxt_c);
-    }
-    // ---------------- modulation: D[128 x 16] = A_hi B_hi + A_lo B_hi + A_hi B_lo ----------------
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint32_t d = tmem + (uint32_t)((it & 1) * 16);
-      const uint32_t a_hi = ptx::smem_u32(aplane), a_lo = a_hi + S::APLANE;
-      const uint32_t b_hi = ptx::smem_u32(bplane), b_lo = b_hi + S::BPLANE;
+    ptx::tc_fence_before();  // also orders this thread's tcgen05.ld of the previous epilogue before the next MMAs
+    ptx::mbar_arrive(afull);
+    if (warp == 0) {
+      if (lane == 0) {
+        // ---------------- modulation: D[128 x 32] = h1 [c1 | c2];  D[:, 0:16] += h2 (2^-11 c1) ----------------
+        ptx::mbar_wait(afull, (uint32_t)(it & 1));
+        ptx::tc_fence_after();
+        const uint32_t d = tmem + (uint32_t)((it & 1) * 32);
+        const uint32_t a1 = ptx::smem_u32(aplane), a2 = a1 + S::APLANE;
+        const uint32_t b_cat = ptx::smem_u32(bcat), b_res = ptx::smem_u32(bres);
+        constexpr uint32_t idesc32 = ptx::umma_idesc_f16(128, 32), idesc16 = ptx::umma_idesc_f16(128, 16);
 #pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t a = (term == 1) ? a_lo : a_hi;
-        const uint32_t bb = (term == 2) ? b_lo : b_hi;
+        for (int ks = 0; ks < 2; ++ks)
+          ptx::umma_f16(d, ptx::umma_desc(a1 + ks * 2 * kF16LboA, kF16LboA, kF16SboA), ptx::umma_desc(b_cat + ks * 2 * 512, 512, 128),
+                        idesc32, ks != 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          ptx::umma_tf32(d, ptx::umma_desc(a + ks * 2 * kF16LboA, kF16LboA, kF16Sbo), ptx::umma_desc(bb + ks * 2 * 256, 256, kF16Sbo),
-                         idesc, (term | ks) != 0);
+        for (int ks = 0; ks < 2; ++ks)
+          ptx::umma_f16(d, ptx::umma_desc(a2 + ks * 2 * kF16LboA, kF16LboA, kF16SboA), ptx::umma_desc(b_res + ks * 2 * 256, 256, 128),
+                        idesc16, true);
+        ptx::umma_commit(mma_bar);
       }
-      ptx::umma_commit(mma_bar);
+      __syncwarp();
+      // x window `buf` is free once all four warps released it: stage the tile NXBUF iterations ahead
+      const long next = tile + (long)S::NXBUF * stride;
+      if (next < p.n_tiles) {
+        ptx::mbar_wait(&xempty[buf], (uint32_t)((it >> 1) & 1));
+        stage_tile(nxt_b, nxt_c, buf);
+      }
+      advance(nxt_b, nxt_c);
+      __syncwarp();
     }
     // ---------------- epilogue of the PREVIOUS tile overlaps this tile's MMAs ----------------
     if (it > 0) {
@@ -287,7 +326,7 @@ __global__ void __launch_bounds__(kF16Threads, (QN <= 12) ? 4 : 3) f16_analysis_
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 32);
+  if (warp == 0) ptx::tmem_dealloc(tmem, 64);
 }
 
 inline bool fast16_analysis_ok(const float* x, const float* y, long T, long F) {
@@ -298,7 +337,7 @@ template <int QLO, int QN>
 int f16_launch_analysis(const F16AnalysisParams& p, cudaStream_t st) {
   using S = F16AnalysisSmem<QN>;
   auto kern = f16_analysis_kernel<QLO, QN>;
-  constexpr int kCtasPerSm = (QN <= 12) ? 4 : 3;  // matches __launch_bounds__ and the shared-memory footprint
+  constexpr int kCtasPerSm = 4;  // matches __launch_bounds__ and the shared-memory footprint
   static int sm_count[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -2,6 +2,7 @@
 // No torch types, no allocation on the device-pointer entry points, no synchronisation.
 #include "../../include/pqmf_b200.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -164,19 +165,13 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   for (int k = 0; k < M; ++k)
     for (int r = 0; r < R; ++r)
       C[(size_t)k * R + r] = 2.0 * std::cos((2 * k + 1) * pi / (2.0 * M) * (r - c0) + ((k & 1) ? -pi / 4 : pi / 4));
-  // tf32 split: hi = round-to-nearest on 13 dropped mantissa bits, lo = tf32(C - hi)
-  auto tf32_rn = [](float v) {
-    uint32_t u;
-    std::memcpy(&u, &v, 4);
-    u = (u + 0x1000u) & 0xffffe000u;
-    float r;
-    std::memcpy(&r, &u, 4);
-    return r;
-  };
+  // two-term fp16 split of the modulation matrix: C = c1 + c2 with c1 = fp16(C), c2 = fp16(C - c1) (both stored as
+  // floats that are exactly representable in fp16); the kernels pair it with a two-term fp16 split of the data and
+  // drop only the (lo x lo) product, i.e. ~2^-23 relative: the tensor-core modulation is exact to fp32 level.
   for (size_t i = 0; i < (size_t)M * R; ++i) {
-    const float hi = tf32_rn((float)C[i]);
+    const float hi = __half2float(__float2half_rn((float)C[i]));
     chi[i] = hi;
-    clo[i] = tf32_rn((float)(C[i] - (double)hi));
+    clo[i] = __half2float(__float2half_rn((float)(C[i] - (double)hi)));
   }
   double res = 0.0;
   for (int k = 0; k < M; ++k)

@@ -1,6 +1,7 @@
 // Thin inline-PTX wrappers for the sm_100a features the fast kernels use: mbarrier, 1-D bulk
 // async copy (TMA engine, UBLKCP), tcgen05 (UMMA) with TMEM accumulators, packed fp32 FMA.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -82,6 +83,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// instruction descriptor for kind::f16 with fp16 A/B, fp32 accumulate, A and B K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands (K = 16 per instruction); issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -119,6 +133,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- packed fp32 (FFMA2) ----
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// ---- two-term fp16 split of an fp32 pair: v = h1 + 2^-11 * h2 (+ ~2^-23 |v|) ----
+// h1 = fp16(v) (round to nearest), h2 = fp16((v - h1) * 2^11): the residual is exact in fp32 and scaled into the fp16
+// normal range; the matching B operand carries the 2^-11.  Returned as packed half2 bit patterns.
+__device__ __forceinline__ void split_f16x2(float2 v, uint32_t& h1_bits, uint32_t& h2_bits) {
+  const __half2 h1 = __floats2half2_rn(v.x, v.y);
+  const float2 h1f = __half22float2(h1);
+  const float2 t = __ffma2_rn(h1f, make_float2(-1.f, -1.f), v);
+  const float2 t2 = __ffma2_rn(t, make_float2(2048.f, 2048.f), make_float2(0.f, 0.f));
+  const __half2 h2 = __floats2half2_rn(t2.x, t2.y);
+  h1_bits = *reinterpret_cast<const uint32_t*>(&h1);
+  h2_bits = *reinterpret_cast<const uint32_t*>(&h2);
+}
 
 }  // namespace ptx
 }  // namespace pqmf
