@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -72,12 +73,13 @@ struct F16AnalysisParams {
   int parity;            // global parity of frame 0
   long tiles_per_row;
   long n_tiles;
+  int debug;             // experiment toggles (PQMF_DEBUG env): 1 = no x reloads, 2 = no stores, 4 = no MMA wait
 };
 
 template <int QN>
 struct F16AnalysisSmem {
   static constexpr int XS = 32 * (64 + QN);     // floats per x window
-  static constexpr int NXBUF = 2;
+  static constexpr int NXBUF = 3;
   static constexpr int APLANE = 4 * kF16LboA;   // one fp16 plane of the A operand [128 x 32]
   static constexpr int BCAT = 4 * 512;          // B = [c1 | c2]: N = 32 rows x K = 32 fp16, 4 K-chunks x (32 rows x 16 B)
   static constexpr int BRES = 4 * 256;          // B = 2^-11 c1 : N = 16 rows x K = 32 fp16
@@ -85,7 +87,7 @@ struct F16AnalysisSmem {
   static constexpr int OFF_A = OFF_X + NXBUF * XS * 4;
   static constexpr int OFF_B = OFF_A + 2 * APLANE;
   static constexpr int OFF_BAR = OFF_B + BCAT + BRES;
-  static constexpr int BYTES = OFF_BAR + 64;
+  static constexpr int BYTES = OFF_BAR + 128;  // 2 NXBUF + 2 mbarriers, the TMEM base slot
 };
 
 // Synchronisation is mbarrier-only inside the tile loop (no __syncthreads): warps drift freely and only meet where
@@ -94,7 +96,8 @@ struct F16AnalysisSmem {
 //   xempty[b] (4 warps)   fold -> TMA issuer : all four warps are done reading window b
 //   afull     (128 thr)   split -> MMA issuer: the A planes of this tile are complete (and D of tile t-1 was drained)
 //   mma_bar   (commit)    MMA -> everyone    : tile's MMAs retired: A planes reusable, D readable
-// Warp 0 doubles as TMA issuer + MMA issuer (one elected lane); it is the only warp that ever waits on other warps.
+// Warp 0 doubles as MMA issuer and warp 3 as TMA issuer (one elected lane each); they are the only warps that ever
+// wait on other warps.  The TMA for tile t + NXBUF is issued as soon as the fold of tile t has released its window.
 template <int QLO, int QN>
 __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16AnalysisParams p) {
   using S = F16AnalysisSmem<QN>;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
       ++b;
     }
   };
-  // WARP 0 ONLY: zero the out-of-range part of an edge window (all lanes), then one lane arms the barrier and
+  // TMA WARP ONLY: zero the out-of-range part of an edge window (all lanes), then one lane arms the barrier and
   // issues the TMA bulk copies.  The arrive releases the zero fill to the waiting warps.
   auto stage_tile = [&](unsigned b, unsigned c, int buf) {
     const long n0 = (long)c * kF16TileFrames;
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const float v = __uint_as_float(r[k]) + __uint_as_float(r[16 + k]);
-        __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
+        if (!(p.debug & 2)) __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
       }
     }
     // streaming: the CTA that owns the last tile of a row also rolls that row's history
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
   const long first = blockIdx.x, stride = gridDim.x;
   unsigned cur_b = blockIdx.x / tpr, cur_c = blockIdx.x % tpr;  // tile being folded
   unsigned nxt_b = cur_b, nxt_c = cur_c;                        // tile being staged (NXBUF iterations ahead)
-  if (warp == 0) {  // prologue: stage the first NXBUF tiles
+  constexpr int kTmaWarp = 3;
+  if (warp == kTmaWarp) {  // prologue: stage the first NXBUF tiles
     for (int i = 0; i < S::NXBUF; ++i) {
       const long tile = first + (long)i * stride;
       if (tile < p.n_tiles) stage_tile(nxt_b, nxt_c, i);
@@ -234,11 +238,12 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
     }
   }
 
-  long it = 0;
+  unsigned it = 0;
   unsigned prev_b = 0, prev_c = 0;
   for (long tile = first; tile < p.n_tiles; tile += stride, ++it) {
-    const int buf = (int)(it & 1);
-    ptx::mbar_wait(&xfull[buf], (uint32_t)((it >> 1) & 1));
+    const int buf = (int)(it % S::NXBUF);
+    const uint32_t xphase = (it / S::NXBUF) & 1;
+    if (!(p.debug & 1) || it < S::NXBUF) ptx::mbar_wait(&xfull[buf], xphase);
 
     // ---------------- fold: 32 FMA / sample on packed fp32 ----------------
     float2 ve[J], vo[J];
@@ -259,8 +264,18 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
     }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&xempty[buf]);  // this warp no longer reads x window `buf`
+    if (warp == kTmaWarp) {
+      // x window `buf` is free once all four warps released it: stage the tile NXBUF iterations ahead
+      const long next = tile + (long)S::NXBUF * stride;
+      if (next < p.n_tiles && !(p.debug & 1)) {
+        ptx::mbar_wait(&xempty[buf], xphase);
+        stage_tile(nxt_b, nxt_c, buf);
+      }
+      advance(nxt_b, nxt_c);
+      __syncwarp();
+    }
     // the previous tile's MMAs must have finished reading the A planes before they are overwritten
-    if (it > 0) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
+    if (it > 0 && !(p.debug & 4)) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
     // ---------------- two-term fp16 split, stored as the UMMA A operand (h1 plane, h2 plane) ----------------
     {
       const int po = (pp + 8) & 15;  // K position of the odd-frame columns r = (phi + 16) mod 32
@@ -300,14 +315,6 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
                         idesc16, true);
         ptx::umma_commit(mma_bar);
       }
-      __syncwarp();
-      // x window `buf` is free once all four warps released it: stage the tile NXBUF iterations ahead
-      const long next = tile + (long)S::NXBUF * stride;
-      if (next < p.n_tiles) {
-        ptx::mbar_wait(&xempty[buf], (uint32_t)((it >> 1) & 1));
-        stage_tile(nxt_b, nxt_c, buf);
-      }
-      advance(nxt_b, nxt_c);
       __syncwarp();
     }
     // ---------------- epilogue of the PREVIOUS tile overlaps this tile's MMAs ----------------
@@ -364,6 +371,10 @@ inline int fast16_analysis(const float* x, const float* hist, float* y, float* h
   p.T = T; p.F = F; p.B = B; p.off = off; p.parity = parity & 1;
   p.tiles_per_row = (F + kF16TileFrames - 1) / kF16TileFrames;
   p.n_tiles = p.tiles_per_row * B;
+  {
+    const char* dbg = getenv("PQMF_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   if (hist != nullptr && ((uintptr_t)hist % 16 || (uintptr_t)hist_out % 16)) return -2;
   const F16Taps t = fast16_taps_from_flags(flags);
   if (t.qn == 12) return f16_launch_analysis<2, 12>(p, st);

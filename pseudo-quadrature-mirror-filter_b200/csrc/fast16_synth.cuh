@@ -126,8 +126,10 @@ __global__ void __launch_bounds__(kF16SynThreads, 2) f16_synthesis_kernel(F16Syn
   const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
 
-  // this thread's sub-band frame (row tid of the tile): 16 bands, sign mask applied at load time
+  // this thread's sub-band frame (row tid of the tile): 16 bands; the sign mask is applied where the values are consumed
+  // (not here: touching v[] right after the loads would stall on them and defeat the prefetch)
   float v[16];
+  bool flip = false;
   auto load_row = [&](unsigned bb, unsigned cc) {
     const long mlo = (long)p.i_off + (long)NI * cc - QLO - QN;  // first frame pair of the tile
     const long n = 2 * mlo + tid - p.shift;                     // true frame index of row tid
@@ -143,10 +145,7 @@ __global__ void __launch_bounds__(kF16SynThreads, 2) f16_synthesis_kernel(F16Syn
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = 0.f;
     }
-    if (((n + p.parity) & 1) == 0) {
-#pragma unroll
-      for (int k = 1; k < 16; k += 2) v[k] = -v[k];
-    }
+    flip = ((n + p.parity) & 1) == 0;
   };
   if ((long)blockIdx.x < p.n_tiles) load_row(b, c);
 
@@ -155,6 +154,10 @@ __global__ void __launch_bounds__(kF16SynThreads, 2) f16_synthesis_kernel(F16Syn
     const long i0 = (long)p.i_off + (long)NI * c;   // first output row of the tile
     // ---------------- two-term fp16 split, stored as UMMA A operand (row tid, 2 K-chunks of 8 bands, 2 planes) ----------------
     {
+      if (flip) {
+#pragma unroll
+        for (int k = 1; k < 16; k += 2) v[k] = -v[k];
+      }
       unsigned char* arow = aplane + tid * 16;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
