@@ -108,6 +108,9 @@ int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host,
                             const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
                             int device);
 
+/* Frees the per-device staging buffers / streams that pqmf_roundtrip_host_f32 keeps between calls. */
+void pqmf_host_release(void);
+
 /* Number of kernels the library has launched in this process (bench.py reports it as gpu_launches). */
 unsigned long long pqmf_launch_count(void);
 

@@ -117,6 +117,20 @@ int roll_history(const float* old_h, const float* blk, float* new_h, long rows, 
 
 bool bad_dims(int B, long n, int M, int L) { return B < 0 || n < 0 || M < 2 || L < M || L > (1 << 16); }
 
+// per-device staging workspace of the host-buffer entry point (pqmf_roundtrip_host_f32)
+constexpr int kHostSlots = 4, kMaxDevices = 16;
+struct HostWorkspace {
+  cudaStream_t st[kHostSlots] = {};
+  float* d_x[kHostSlots] = {};
+  float* d_y[kHostSlots] = {};
+  float* d_o[kHostSlots] = {};
+  float* d_bank = nullptr;
+  size_t chunk_elems = 0, bank_elems = 0;
+  bool streams_ready = false;
+};
+HostWorkspace g_host_ws[kMaxDevices];
+std::mutex g_host_mutex;
+
 bool use_fast(int M, int L, const float* tables, unsigned flags) {
   return tables != nullptr && !(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_NO_SIGN)) && pqmf::fast16_supported(M, L);
 }
@@ -261,58 +275,88 @@ int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host,
   if (bad_dims(B, T, M, L) || !x_host || !out_host || !hk_host || (T % M) != 0) return PQMF_ERR_ARG;
   if (B == 0 || T == 0) return PQMF_OK;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return PQMF_ERR_NO_DEVICE;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || device >= kMaxDevices) return PQMF_ERR_NO_DEVICE;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return (int)e;
   const long F = T / M;
-  // Row chunks sized ~32 MiB of input so that H2D(i+1), kernels(i) and D2H(i-1) overlap (PCIe is full duplex).
-  long rows_per_chunk = (32L << 20) / (T * (long)sizeof(float));
+  // Row chunks of ~16 MiB of input: H2D(i+1), the two kernels of chunk i and D2H(i-1) overlap (PCIe is full duplex),
+  // each chunk on its own stream.  The staging buffers live in a per-device workspace that is created on first use
+  // and only ever grows, so steady-state calls do no allocation.
+  long rows_per_chunk = (16L << 20) / (T * (long)sizeof(float));
   if (rows_per_chunk < 1) rows_per_chunk = 1;
   if (rows_per_chunk > B) rows_per_chunk = B;
-  const int n_buf = 3;
   const size_t chunk_elems = (size_t)rows_per_chunk * T;
   const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
-  float *d_hk = nullptr, *d_tab = nullptr, *d_x[n_buf] = {}, *d_y[n_buf] = {}, *d_o[n_buf] = {};
-  cudaStream_t st[n_buf] = {};
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  HostWorkspace& ws = g_host_ws[device];
   int rc = PQMF_OK;
   auto check = [&](cudaError_t err) { if (err != cudaSuccess && rc == PQMF_OK) rc = (int)err; return err == cudaSuccess; };
-  check(cudaMalloc(&d_hk, (size_t)M * L * sizeof(float)));
-  if (n_tab) check(cudaMalloc(&d_tab, (size_t)n_tab * sizeof(float)));
-  for (int i = 0; i < n_buf && rc == PQMF_OK; ++i) {
-    check(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    check(cudaMalloc(&d_x[i], chunk_elems * sizeof(float)));
-    check(cudaMalloc(&d_y[i], chunk_elems * sizeof(float)));
-    check(cudaMalloc(&d_o[i], chunk_elems * sizeof(float)));
+  if (!ws.streams_ready) {
+    for (int i = 0; i < kHostSlots; ++i) check(cudaStreamCreateWithFlags(&ws.st[i], cudaStreamNonBlocking));
+    ws.streams_ready = (rc == PQMF_OK);
   }
-  if (rc == PQMF_OK) {
-    check(cudaMemcpy(d_hk, hk_host, (size_t)M * L * sizeof(float), cudaMemcpyHostToDevice));
-    if (n_tab) check(cudaMemcpy(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice));
+  if (rc == PQMF_OK && ws.chunk_elems < chunk_elems) {
+    for (int i = 0; i < kHostSlots; ++i) {
+      if (ws.d_x[i]) cudaFree(ws.d_x[i]);
+      if (ws.d_y[i]) cudaFree(ws.d_y[i]);
+      if (ws.d_o[i]) cudaFree(ws.d_o[i]);
+      ws.d_x[i] = ws.d_y[i] = ws.d_o[i] = nullptr;
+      check(cudaMalloc(&ws.d_x[i], chunk_elems * sizeof(float)));
+      check(cudaMalloc(&ws.d_y[i], chunk_elems * sizeof(float)));
+      check(cudaMalloc(&ws.d_o[i], chunk_elems * sizeof(float)));
+    }
+    ws.chunk_elems = (rc == PQMF_OK) ? chunk_elems : 0;
   }
+  const size_t bank_elems = (size_t)M * L;
+  if (rc == PQMF_OK && ws.bank_elems < bank_elems + (size_t)n_tab) {
+    if (ws.d_bank) cudaFree(ws.d_bank);
+    ws.d_bank = nullptr;
+    check(cudaMalloc(&ws.d_bank, (bank_elems + (size_t)n_tab) * sizeof(float)));
+    ws.bank_elems = (rc == PQMF_OK) ? bank_elems + (size_t)n_tab : 0;
+  }
+  if (rc != PQMF_OK) return rc;
+  float* d_hk = ws.d_bank;
+  float* d_tab = n_tab ? ws.d_bank + bank_elems : nullptr;
+  // the bank is tiny (<= a few hundred KB): re-send it with every call instead of tracking caller-side changes
+  check(cudaMemcpyAsync(d_hk, hk_host, bank_elems * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
+  if (n_tab) check(cudaMemcpyAsync(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
+  check(cudaStreamSynchronize(ws.st[0]));
   int slot = 0;
-  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += rows_per_chunk, slot = (slot + 1) % n_buf) {
+  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += rows_per_chunk, slot = (slot + 1) % kHostSlots) {
     const int rows = (int)((B - r0 < rows_per_chunk) ? (B - r0) : rows_per_chunk);
     const size_t n = (size_t)rows * T;
-    cudaStream_t s = st[slot];
-    check(cudaMemcpyAsync(d_x[slot], x_host + (size_t)r0 * T, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    cudaStream_t s = ws.st[slot];
+    check(cudaMemcpyAsync(ws.d_x[slot], x_host + (size_t)r0 * T, n * sizeof(float), cudaMemcpyHostToDevice, s));
     if (rc) break;
-    rc = pqmf_analysis_f32(d_x[slot], d_y[slot], d_hk, d_tab, rows, T, F, M, L, flags, s);
+    rc = pqmf_analysis_f32(ws.d_x[slot], ws.d_y[slot], d_hk, d_tab, rows, T, F, M, L, flags, s);
     if (rc) break;
-    rc = pqmf_synthesis_f32(d_y[slot], d_o[slot], d_hk, d_tab, rows, F, M, L, delay_frames, flags, s);
+    rc = pqmf_synthesis_f32(ws.d_y[slot], ws.d_o[slot], d_hk, d_tab, rows, F, M, L, delay_frames, flags, s);
     if (rc) break;
-    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * T, d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    check(cudaMemcpyAsync(out_host + (size_t)r0 * T, d_o[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * T, ws.d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    check(cudaMemcpyAsync(out_host + (size_t)r0 * T, ws.d_o[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
-  for (int i = 0; i < n_buf; ++i)
-    if (st[i]) check(cudaStreamSynchronize(st[i]));
-  for (int i = 0; i < n_buf; ++i) {
-    if (d_x[i]) cudaFree(d_x[i]);
-    if (d_y[i]) cudaFree(d_y[i]);
-    if (d_o[i]) cudaFree(d_o[i]);
-    if (st[i]) cudaStreamDestroy(st[i]);
-  }
-  if (d_hk) cudaFree(d_hk);
-  if (d_tab) cudaFree(d_tab);
+  for (int i = 0; i < kHostSlots; ++i) check(cudaStreamSynchronize(ws.st[i]));
   return rc;
+}
+
+void pqmf_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < kMaxDevices; ++d) {
+    HostWorkspace& ws = g_host_ws[d];
+    if (!ws.streams_ready && !ws.d_bank && !ws.chunk_elems) continue;
+    cudaSetDevice(d);
+    for (int i = 0; i < kHostSlots; ++i) {
+      if (ws.d_x[i]) cudaFree(ws.d_x[i]);
+      if (ws.d_y[i]) cudaFree(ws.d_y[i]);
+      if (ws.d_o[i]) cudaFree(ws.d_o[i]);
+      if (ws.streams_ready && ws.st[i]) cudaStreamDestroy(ws.st[i]);
+    }
+    if (ws.d_bank) cudaFree(ws.d_bank);
+    ws = HostWorkspace{};
+  }
+  cudaSetDevice(cur);
 }
 
 }  // extern "C"
