@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -73,7 +74,7 @@ struct F16AnalysisParams {
   int parity;            // global parity of frame 0
   long tiles_per_row;
   long n_tiles;
-  int debug;             // experiment toggles (PQMF_DEBUG env): 1 = no x reloads, 2 = no stores, 4 = no MMA wait
+  int num_sms;           // CTAs are launched num_sms at a time: slot of a CTA on its SM = blockIdx.x / num_sms
 };
 
 template <int QN>
@@ -98,7 +99,7 @@ struct F16AnalysisSmem {
 //   mma_bar   (commit)    MMA -> everyone    : tile's MMAs retired: A planes reusable, D readable
 // Warp 0 doubles as MMA issuer and warp 3 as TMA issuer (one elected lane each); they are the only warps that ever
 // wait on other warps.  The TMA for tile t + NXBUF is issued as soon as the fold of tile t has released its window.
-template <int QLO, int QN>
+template <int QLO, int QN, int V>
 __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16AnalysisParams p) {
   using S = F16AnalysisSmem<QN>;
   constexpr int J = kF16J;
@@ -118,12 +119,14 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
   const int pp = lane & 15;              // phase pair: phases 2pp, 2pp+1
   const int mg = warp * 2 + (lane >> 4);  // m-group: frame pairs [8 mg, 8 mg + 8)
   const int phi = 2 * pp;
+  const int mma_warp = (V & 4) ? (int)((blockIdx.x / (unsigned)p.num_sms) & 3u) : 0;
+  const int kTmaWarp = (V & 4) ? ((mma_warp + 2) & 3) : 3;
 
   // ---- one-time setup: barriers, TMEM, B operands in UMMA K-major layout, taps in registers ----
   if (tid == 0) {
     for (int i = 0; i < S::NXBUF; ++i) {
       ptx::mbar_init(&xfull[i], 1);
-      ptx::mbar_init(&xempty[i], kF16Threads / 32);
+      ptx::mbar_init(&xempty[i], (V & 8) ? kF16Threads : kF16Threads / 32);
     }
     ptx::mbar_init(afull, kF16Threads);
     ptx::mbar_init(mma_bar, 1);
@@ -213,7 +216,12 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const float v = __uint_as_float(r[k]) + __uint_as_float(r[16 + k]);
-        if (!(p.debug & 2)) __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
+        if (V & 1) {
+          __stcs(yp, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
+          yp += p.F;
+        } else {
+          __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
+        }
       }
     }
     // streaming: the CTA that owns the last tile of a row also rolls that row's history
@@ -229,7 +237,6 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
   const long first = blockIdx.x, stride = gridDim.x;
   unsigned cur_b = blockIdx.x / tpr, cur_c = blockIdx.x % tpr;  // tile being folded
   unsigned nxt_b = cur_b, nxt_c = cur_c;                        // tile being staged (NXBUF iterations ahead)
-  constexpr int kTmaWarp = 3;
   if (warp == kTmaWarp) {  // prologue: stage the first NXBUF tiles
     for (int i = 0; i < S::NXBUF; ++i) {
       const long tile = first + (long)i * stride;
@@ -240,10 +247,23 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
 
   unsigned it = 0;
   unsigned prev_b = 0, prev_c = 0;
+  int ibuf = 0;
+  uint32_t iphase = 0;
   for (long tile = first; tile < p.n_tiles; tile += stride, ++it) {
-    const int buf = (int)(it % S::NXBUF);
-    const uint32_t xphase = (it / S::NXBUF) & 1;
-    if (!(p.debug & 1) || it < S::NXBUF) ptx::mbar_wait(&xfull[buf], xphase);
+    int buf;
+    uint32_t xphase;
+    if (V & 2) {
+      buf = ibuf;
+      xphase = iphase;
+      if (++ibuf == S::NXBUF) {
+        ibuf = 0;
+        iphase ^= 1;
+      }
+    } else {
+      buf = (int)(it % S::NXBUF);
+      xphase = (it / S::NXBUF) & 1;
+    }
+    ptx::mbar_wait(&xfull[buf], xphase);
 
     // ---------------- fold: 32 FMA / sample on packed fp32 ----------------
     float2 ve[J], vo[J];
@@ -262,12 +282,16 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&xempty[buf]);  // this warp no longer reads x window `buf`
+    if (V & 8) {
+      ptx::mbar_arrive(&xempty[buf]);
+    } else {
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&xempty[buf]);  // this warp no longer reads x window `buf`
+    }
     if (warp == kTmaWarp) {
       // x window `buf` is free once all four warps released it: stage the tile NXBUF iterations ahead
       const long next = tile + (long)S::NXBUF * stride;
-      if (next < p.n_tiles && !(p.debug & 1)) {
+      if (next < p.n_tiles) {
         ptx::mbar_wait(&xempty[buf], xphase);
         stage_tile(nxt_b, nxt_c, buf);
       }
@@ -275,7 +299,7 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
       __syncwarp();
     }
     // the previous tile's MMAs must have finished reading the A planes before they are overwritten
-    if (it > 0 && !(p.debug & 4)) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
+    if (it > 0) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
     // ---------------- two-term fp16 split, stored as the UMMA A operand (h1 plane, h2 plane) ----------------
     {
       const int po = (pp + 8) & 15;  // K position of the odd-frame columns r = (phi + 16) mod 32
@@ -296,7 +320,7 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
     ptx::fence_proxy_async();
     ptx::tc_fence_before();  // also orders this thread's tcgen05.ld of the previous epilogue before the next MMAs
     ptx::mbar_arrive(afull);
-    if (warp == 0) {
+    if (warp == mma_warp) {
       if (lane == 0) {
         // ---------------- modulation: D[128 x 32] = h1 [c1 | c2];  D[:, 0:16] += h2 (2^-11 c1) ----------------
         ptx::mbar_wait(afull, (uint32_t)(it & 1));
@@ -340,10 +364,10 @@ inline bool fast16_analysis_ok(const float* x, const float* y, long T, long F) {
   return (T % 16) == 0 && F == T / 16 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 4) == 0 && T > 0;
 }
 
-template <int QLO, int QN>
-int f16_launch_analysis(const F16AnalysisParams& p, cudaStream_t st) {
+template <int QLO, int QN, int V>
+int f16_launch_analysis(F16AnalysisParams p, cudaStream_t st) {
   using S = F16AnalysisSmem<QN>;
-  auto kern = f16_analysis_kernel<QLO, QN>;
+  auto kern = f16_analysis_kernel<QLO, QN, V>;
   constexpr int kCtasPerSm = 4;  // matches __launch_bounds__ and the shared-memory footprint
   static int sm_count[64] = {0};
   int dev = 0;
@@ -359,6 +383,7 @@ int f16_launch_analysis(const F16AnalysisParams& p, cudaStream_t st) {
   if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
   long grid = (long)sm_count[dev] * kCtasPerSm;
   if (grid > p.n_tiles) grid = p.n_tiles;
+  p.num_sms = sm_count[dev];
   kern<<<(unsigned)grid, kF16Threads, S::BYTES, st>>>(p);
   return (int)cudaGetLastError();
 }
@@ -371,14 +396,20 @@ inline int fast16_analysis(const float* x, const float* hist, float* y, float* h
   p.T = T; p.F = F; p.B = B; p.off = off; p.parity = parity & 1;
   p.tiles_per_row = (F + kF16TileFrames - 1) / kF16TileFrames;
   p.n_tiles = p.tiles_per_row * B;
-  {
-    const char* dbg = getenv("PQMF_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
   if (hist != nullptr && ((uintptr_t)hist % 16 || (uintptr_t)hist_out % 16)) return -2;
   const F16Taps t = fast16_taps_from_flags(flags);
-  if (t.qn == 12) return f16_launch_analysis<2, 12>(p, st);
-  return f16_launch_analysis<0, 16>(p, st);
+  if (t.qn == 12) {
+    const char* ev = getenv("PQMF_VARIANT");  // TEMPORARY: A/B switch for kernel variants
+    switch (ev ? atoi(ev) : 0) {
+      case 1: return f16_launch_analysis<2, 12, 1>(p, st);
+      case 2: return f16_launch_analysis<2, 12, 2>(p, st);
+      case 4: return f16_launch_analysis<2, 12, 4>(p, st);
+      case 8: return f16_launch_analysis<2, 12, 8>(p, st);
+      case 15: return f16_launch_analysis<2, 12, 15>(p, st);
+      default: return f16_launch_analysis<2, 12, 0>(p, st);
+    }
+  }
+  return f16_launch_analysis<0, 16, 0>(p, st);
 }
 
 }  // namespace pqmf
