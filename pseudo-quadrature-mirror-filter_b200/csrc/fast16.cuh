@@ -24,8 +24,6 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
-#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -99,7 +97,7 @@ struct F16AnalysisSmem {
 //   mma_bar   (commit)    MMA -> everyone    : tile's MMAs retired: A planes reusable, D readable
 // Warp 0 doubles as MMA issuer and warp 3 as TMA issuer (one elected lane each); they are the only warps that ever
 // wait on other warps.  The TMA for tile t + NXBUF is issued as soon as the fold of tile t has released its window.
-template <int QLO, int QN, int V>
+template <int QLO, int QN>
 __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16AnalysisParams p) {
   using S = F16AnalysisSmem<QN>;
   constexpr int J = kF16J;
@@ -119,14 +117,13 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
   const int pp = lane & 15;              // phase pair: phases 2pp, 2pp+1
   const int mg = warp * 2 + (lane >> 4);  // m-group: frame pairs [8 mg, 8 mg + 8)
   const int phi = 2 * pp;
-  const int mma_warp = (V & 4) ? (int)((blockIdx.x / (unsigned)p.num_sms) & 3u) : 0;
-  const int kTmaWarp = (V & 4) ? ((mma_warp + 2) & 3) : 3;
+  constexpr int mma_warp = 0, kTmaWarp = 3;
 
   // ---- one-time setup: barriers, TMEM, B operands in UMMA K-major layout, taps in registers ----
   if (tid == 0) {
     for (int i = 0; i < S::NXBUF; ++i) {
       ptx::mbar_init(&xfull[i], 1);
-      ptx::mbar_init(&xempty[i], (V & 8) ? kF16Threads : kF16Threads / 32);
+      ptx::mbar_init(&xempty[i], kF16Threads);
     }
     ptx::mbar_init(afull, kF16Threads);
     ptx::mbar_init(mma_bar, 1);
@@ -216,12 +213,7 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const float v = __uint_as_float(r[k]) + __uint_as_float(r[16 + k]);
-        if (V & 1) {
-          __stcs(yp, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
-          yp += p.F;
-        } else {
-          __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
-        }
+        __stcs(yp + (size_t)k * p.F, __uint_as_float(__float_as_uint(v) ^ ((k & 1) ? flip : 0u)));
       }
     }
     // streaming: the CTA that owns the last tile of a row also rolls that row's history
@@ -247,22 +239,9 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
 
   unsigned it = 0;
   unsigned prev_b = 0, prev_c = 0;
-  int ibuf = 0;
-  uint32_t iphase = 0;
   for (long tile = first; tile < p.n_tiles; tile += stride, ++it) {
-    int buf;
-    uint32_t xphase;
-    if (V & 2) {
-      buf = ibuf;
-      xphase = iphase;
-      if (++ibuf == S::NXBUF) {
-        ibuf = 0;
-        iphase ^= 1;
-      }
-    } else {
-      buf = (int)(it % S::NXBUF);
-      xphase = (it / S::NXBUF) & 1;
-    }
+    const int buf = (int)(it % S::NXBUF);
+    const uint32_t xphase = (it / S::NXBUF) & 1;
     ptx::mbar_wait(&xfull[buf], xphase);
 
     // ---------------- fold: 32 FMA / sample on packed fp32 ----------------
@@ -282,12 +261,7 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
         }
       }
     }
-    if (V & 8) {
-      ptx::mbar_arrive(&xempty[buf]);
-    } else {
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&xempty[buf]);  // this warp no longer reads x window `buf`
-    }
+    ptx::mbar_arrive(&xempty[buf]);  // this thread no longer reads x window `buf`
     if (warp == kTmaWarp) {
       // x window `buf` is free once all four warps released it: stage the tile NXBUF iterations ahead
       const long next = tile + (long)S::NXBUF * stride;
@@ -321,22 +295,23 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
     ptx::tc_fence_before();  // also orders this thread's tcgen05.ld of the previous epilogue before the next MMAs
     ptx::mbar_arrive(afull);
     if (warp == mma_warp) {
-      if (lane == 0) {
-        // ---------------- modulation: D[128 x 32] = h1 [c1 | c2];  D[:, 0:16] += h2 (2^-11 c1) ----------------
-        ptx::mbar_wait(afull, (uint32_t)(it & 1));
-        ptx::tc_fence_after();
+      // ---------------- modulation: D[128 x 32] = h1 [c1 | c2];  D[:, 0:16] += h2 (2^-11 c1) ----------------
+      // the whole warp waits (warp-uniform control flow) and one elected lane issues, so the descriptors stay in uniform
+      // registers (under `if (lane == 0)` ptxas wraps every tcgen05.mma in a uniformisation loop)
+      ptx::mbar_wait(afull, (uint32_t)(it & 1));
+      ptx::tc_fence_after();
+      if (ptx::elect_one_sync()) {
         const uint32_t d = tmem + (uint32_t)((it & 1) * 32);
-        const uint32_t a1 = ptx::smem_u32(aplane), a2 = a1 + S::APLANE;
-        const uint32_t b_cat = ptx::smem_u32(bcat), b_res = ptx::smem_u32(bres);
+        const uint64_t da1 = ptx::umma_desc(ptx::smem_u32(aplane), kF16LboA, kF16SboA);
+        const uint64_t da2 = ptx::umma_desc(ptx::smem_u32(aplane) + S::APLANE, kF16LboA, kF16SboA);
+        const uint64_t db_cat = ptx::umma_desc(ptx::smem_u32(bcat), 512, 128), db_res = ptx::umma_desc(ptx::smem_u32(bres), 256, 128);
         constexpr uint32_t idesc32 = ptx::umma_idesc_f16(128, 32), idesc16 = ptx::umma_idesc_f16(128, 16);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          ptx::umma_f16(d, ptx::umma_desc(a1 + ks * 2 * kF16LboA, kF16LboA, kF16SboA), ptx::umma_desc(b_cat + ks * 2 * 512, 512, 128),
-                        idesc32, ks != 0);
+          ptx::umma_f16(d, da1 + (uint64_t)(ks * 2 * kF16LboA / 16), db_cat + (uint64_t)(ks * 2 * 512 / 16), idesc32, ks != 0);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          ptx::umma_f16(d, ptx::umma_desc(a2 + ks * 2 * kF16LboA, kF16LboA, kF16SboA), ptx::umma_desc(b_res + ks * 2 * 256, 256, 128),
-                        idesc16, true);
+          ptx::umma_f16(d, da2 + (uint64_t)(ks * 2 * kF16LboA / 16), db_res + (uint64_t)(ks * 2 * 256 / 16), idesc16, true);
         ptx::umma_commit(mma_bar);
       }
       __syncwarp();
@@ -364,10 +339,10 @@ inline bool fast16_analysis_ok(const float* x, const float* y, long T, long F) {
   return (T % 16) == 0 && F == T / 16 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 4) == 0 && T > 0;
 }
 
-template <int QLO, int QN, int V>
+template <int QLO, int QN>
 int f16_launch_analysis(F16AnalysisParams p, cudaStream_t st) {
   using S = F16AnalysisSmem<QN>;
-  auto kern = f16_analysis_kernel<QLO, QN, V>;
+  auto kern = f16_analysis_kernel<QLO, QN>;
   constexpr int kCtasPerSm = 4;  // matches __launch_bounds__ and the shared-memory footprint
   static int sm_count[64] = {0};
   int dev = 0;
@@ -398,18 +373,8 @@ inline int fast16_analysis(const float* x, const float* hist, float* y, float* h
   p.n_tiles = p.tiles_per_row * B;
   if (hist != nullptr && ((uintptr_t)hist % 16 || (uintptr_t)hist_out % 16)) return -2;
   const F16Taps t = fast16_taps_from_flags(flags);
-  if (t.qn == 12) {
-    const char* ev = getenv("PQMF_VARIANT");  // TEMPORARY: A/B switch for kernel variants
-    switch (ev ? atoi(ev) : 0) {
-      case 1: return f16_launch_analysis<2, 12, 1>(p, st);
-      case 2: return f16_launch_analysis<2, 12, 2>(p, st);
-      case 4: return f16_launch_analysis<2, 12, 4>(p, st);
-      case 8: return f16_launch_analysis<2, 12, 8>(p, st);
-      case 15: return f16_launch_analysis<2, 12, 15>(p, st);
-      default: return f16_launch_analysis<2, 12, 0>(p, st);
-    }
-  }
-  return f16_launch_analysis<0, 16, 0>(p, st);
+  if (t.qn == 12) return f16_launch_analysis<2, 12>(p, st);
+  return f16_launch_analysis<0, 16>(p, st);
 }
 
 }  // namespace pqmf

@@ -174,18 +174,20 @@ __global__ void __launch_bounds__(kF16SynThreads, 2) f16_synthesis_kernel(F16Syn
     ptx::tc_fence_before();
     ptx::mbar_arrive(afull);
     // ---------------- inverse modulation, per 128-row half: D_h[128 x 64] = h1 [c1|c2]^T ; D_h[:, 0:32] += h2 (2^-11 c1)^T ----------------
-    if (tid == 0) {
+    if (warp == 0) {
       ptx::mbar_wait(afull, (uint32_t)(it & 1));
       ptx::tc_fence_after();
-      const uint32_t a1 = ptx::smem_u32(aplane), a2 = a1 + S::APLANE;
-      const uint64_t d_cat = ptx::umma_desc(ptx::smem_u32(bcat), 1024, 128), d_res = ptx::umma_desc(ptx::smem_u32(bres), 512, 128);
-      constexpr uint32_t idesc64 = ptx::umma_idesc_f16(128, 64), idesc32 = ptx::umma_idesc_f16(128, 32);
+      if (ptx::elect_one_sync()) {
+        const uint32_t a1 = ptx::smem_u32(aplane), a2 = a1 + S::APLANE;
+        const uint64_t d_cat = ptx::umma_desc(ptx::smem_u32(bcat), 1024, 128), d_res = ptx::umma_desc(ptx::smem_u32(bres), 512, 128);
+        constexpr uint32_t idesc64 = ptx::umma_idesc_f16(128, 64), idesc32 = ptx::umma_idesc_f16(128, 32);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        ptx::umma_f16(tmem + half * 64, ptx::umma_desc(a1 + half * 128 * 16, kF16SynLboA, 128), d_cat, idesc64, false);
-        ptx::umma_f16(tmem + half * 64, ptx::umma_desc(a2 + half * 128 * 16, kF16SynLboA, 128), d_res, idesc32, true);
+        for (int half = 0; half < 2; ++half) {
+          ptx::umma_f16(tmem + half * 64, ptx::umma_desc(a1 + half * 128 * 16, kF16SynLboA, 128), d_cat, idesc64, false);
+          ptx::umma_f16(tmem + half * 64, ptx::umma_desc(a2 + half * 128 * 16, kF16SynLboA, 128), d_res, idesc32, true);
+        }
+        ptx::umma_commit(mma_bar);
       }
-      ptx::umma_commit(mma_bar);
     }
     __syncwarp();
     // streaming: the CTA that owns the last tile of a row rolls that row's sub-band history while the MMAs run

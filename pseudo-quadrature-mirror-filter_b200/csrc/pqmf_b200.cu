@@ -15,6 +15,7 @@
 #include "direct_form.cuh"
 #include "fast16.cuh"
 #include "fast16_synth.cuh"
+#include "hankel16.cuh"
 
 namespace {
 
@@ -131,8 +132,51 @@ struct HostWorkspace {
 HostWorkspace g_host_ws[kMaxDevices];
 std::mutex g_host_mutex;
 
+constexpr long kFoldTableFloats = 512 + 2 * 16 * 32;  // [ g | c1 | c2 ] of the fold + modulation path
+
+// n_band 16 fast path: fold + tensor-core modulation (fast16*.cuh), or -- with PQMF_FLAG_EXACT -- the direct form as an
+// implicit-Hankel GEMM on the tensor cores (hankel16.cuh).  flags bits [8,12) = first active tap / 32, [12,17) = taps / 32.
+int exact_tc_analysis(const float* x, const float* hist, float* y, float* hist_out, const float* tables, int B, long T, long F, int off,
+                  int parity, unsigned flags, cudaStream_t st) {
+  const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
+  pqmf::H16AnalysisParams p{};
+  p.x = x; p.hist = hist; p.y = y; p.hist_out = hist_out;
+  p.bank = reinterpret_cast<const uint16_t*>(tables + kFoldTableFloats);
+  p.T = T; p.F = F; p.off = off; p.parity = parity & 1;
+  p.tiles_per_row = (F + pqmf::kH16Frames - 1) / pqmf::kH16Frames;
+  p.n_tiles = p.tiles_per_row * B;
+  if (hist != nullptr && ((uintptr_t)hist % 16 || (uintptr_t)hist_out % 16)) return PQMF_ERR_UNSUPPORTED;
+  return trimmed ? pqmf::h16_launch_analysis<64, 384>(p, st) : pqmf::h16_launch_analysis<0, 512>(p, st);
+}
+
+int exact_tc_synthesis(const float* s, const float* hist, float* out, float* hist_out, const float* tables, int B, long F, int off2,
+                   int parity, unsigned flags, cudaStream_t st) {
+  const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
+  const int kt = trimmed ? 384 : 512;
+  if (off2 % 16 != 0) return PQMF_ERR_UNSUPPORTED;
+  pqmf::H16SynthesisParams p{};
+  p.s = s; p.hist = hist; p.out = out; p.hist_out = hist_out;
+  p.bank = reinterpret_cast<const uint16_t*>(tables + kFoldTableFloats) + (size_t)kt * 32;
+  p.F = F; p.o = off2 / 16; p.parity = parity & 1;
+  p.tiles_per_row = (F + pqmf::kH16Frames - 1) / pqmf::kH16Frames;
+  p.n_tiles = p.tiles_per_row * B;
+  return trimmed ? pqmf::h16_launch_synthesis<64, 384>(p, st) : pqmf::h16_launch_synthesis<0, 512>(p, st);
+}
+
+int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, const float* tables, int B, long T, long F, int off,
+                  int parity, unsigned flags, cudaStream_t st) {
+  if (flags & PQMF_FLAG_EXACT) return exact_tc_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
+  return pqmf::fast16_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
+}
+
+int fast_synthesis(const float* s, const float* hist, float* out, float* hist_out, const float* tables, int B, long F, int off2,
+                   int parity, unsigned flags, cudaStream_t st) {
+  if (flags & PQMF_FLAG_EXACT) return exact_tc_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
+  return pqmf::fast16_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
+}
+
 bool use_fast(int M, int L, const float* tables, unsigned flags) {
-  return tables != nullptr && !(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_NO_SIGN)) && pqmf::fast16_supported(M, L);
+  return tables != nullptr && !(flags & PQMF_FLAG_NO_SIGN) && pqmf::hankel16_supported(M, L);
 }
 
 }  // namespace
@@ -155,12 +199,14 @@ unsigned long long pqmf_launch_count(void) { return g_launches.load(); }
 
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags) { return use_fast(M, L, tables, flags) ? 1 : 0; }
 
-long pqmf_tables_numel(int M, int L) { return pqmf::fast16_supported(M, L) ? (long)L + 2L * M * 2 * M : 0; }
+long pqmf_tables_numel(int M, int L) { return pqmf::hankel16_supported(M, L) ? kFoldTableFloats + 2L * L * 16 : 0; }
 
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
                           double* residual, unsigned* fast_flags) {
   if (!hk_host || !h_host || !tables_host || N <= 0 || N > L) return PQMF_ERR_ARG;
-  if (!pqmf::fast16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
+  if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
+  std::memset(tables_host, 0, (size_t)pqmf_tables_numel(M, L) * sizeof(float));
+  // ---- part 1: fold + modulation tables  [ g (L) | c1 (M*2M) | c2 (M*2M) ]
   // hk[k, r + 2M q] = (-1)^q * 2 hpad[r + 2M q] * cos((2k+1) pi/(2M) (r - c0) + (-1)^k pi/4)   
   //                 =  g[r + 2M q]              * C[k, r]
   const int pad_l = (L - N) / 2;       // center_pad_next_pow_2, reference pqmf.py:26-32
@@ -179,9 +225,7 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   for (int k = 0; k < M; ++k)
     for (int r = 0; r < R; ++r)
       C[(size_t)k * R + r] = 2.0 * std::cos((2 * k + 1) * pi / (2.0 * M) * (r - c0) + ((k & 1) ? -pi / 4 : pi / 4));
-  // two-term fp16 split of the modulation matrix: C = c1 + c2 with c1 = fp16(C), c2 = fp16(C - c1) (both stored as
-  // floats that are exactly representable in fp16); the kernels pair it with a two-term fp16 split of the data and
-  // drop only the (lo x lo) product, i.e. ~2^-23 relative: the tensor-core modulation is exact to fp32 level.
+  // two-term fp16 split of the modulation matrix: C = c1 + c2 (both exactly representable in fp16)
   for (size_t i = 0; i < (size_t)M * R; ++i) {
     const float hi = __half2float(__float2half_rn((float)C[i]));
     chi[i] = hi;
@@ -194,13 +238,21 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
       res = std::fmax(res, std::fabs((double)hk_host[(size_t)k * L + j] - model));
     }
   if (residual) *residual = res;
-  if (fast_flags) {
-    // taps q in {0,1,14,15} of every 32-sample phase are pure padding when the prototype is short enough
-    bool trimmed = true;
+  // taps that are pure centre padding: with N = 377 of 512 the first and last 64 columns of hk are zero
+  bool trimmed = true;
+  for (int k = 0; k < M && trimmed; ++k)
     for (int j = 0; j < L; ++j)
-      if ((j < 64 || j >= 448) && g[j] != 0.f) trimmed = false;
-    *fast_flags = trimmed ? pqmf::fast16_flags_for_taps(2, 12) : pqmf::fast16_flags_for_taps(0, 16);
-  }
+      if ((j < 64 || j >= 448) && hk_host[(size_t)k * L + j] != 0.f) {
+        trimmed = false;
+        break;
+      }
+  for (int j = 0; j < L; ++j)
+    if ((j < 64 || j >= 448) && g[j] != 0.f) trimmed = false;
+  // ---- part 2: fp16 images of hk itself for the exact tensor-core path (hankel16.cuh)
+  const int jlo = trimmed ? 64 : 0, kt = trimmed ? 384 : 512;
+  uint16_t* img = reinterpret_cast<uint16_t*>(tables_host + kFoldTableFloats);
+  pqmf::hankel16_build_banks(hk_host, jlo, kt, img, img + (size_t)kt * 32);
+  if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32);
   return PQMF_OK;
 }
 
@@ -210,8 +262,8 @@ int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* ta
   if (B == 0 || n_frames == 0) return PQMF_OK;
   if (!x || !y || !hk) return PQMF_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_fast(M, L, tables, flags) && pqmf::fast16_analysis_ok(x, y, T, n_frames)) {
-    int e = pqmf::fast16_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, flags, st);
+  if (use_fast(M, L, tables, flags) && pqmf::hankel16_analysis_ok(x, y, T, n_frames)) {
+    int e = fast_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   return analysis_direct(x, nullptr, y, hk, B, T, n_frames, M, L, L / 2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
@@ -224,8 +276,8 @@ int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float*
   if (!s || !out || !hk) return PQMF_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int off2 = L / 2 - delay_frames * M;
-  if (use_fast(M, L, tables, flags) && pqmf::fast16_synthesis_ok(s, out, n_frames)) {
-    int e = pqmf::fast16_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, flags, st);
+  if (use_fast(M, L, tables, flags) && pqmf::hankel16_synthesis_ok(s, out, n_frames)) {
+    int e = fast_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   return synthesis_direct(s, nullptr, out, hk, B, n_frames, M, L, off2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
@@ -241,8 +293,8 @@ int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const fl
   if (!x || !y) return PQMF_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const long F = T / M;
-  if (use_fast(M, L, tables, flags) && pqmf::fast16_analysis_ok(x, y, T, F)) {
-    int e = pqmf::fast16_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, flags, st);
+  if (use_fast(M, L, tables, flags) && pqmf::hankel16_analysis_ok(x, y, T, F)) {
+    int e = fast_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   int e = analysis_direct(x, state_in, y, hk, B, T, F, M, L, L, frame_parity, 0, st);
@@ -260,8 +312,8 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
   cudaStream_t st = (cudaStream_t)stream;
   const int K = L / M;
   // history frames sit K frames before frame 0 of the block: their parity offset is (frame_parity - K)
-  if (use_fast(M, L, tables, flags) && pqmf::fast16_synthesis_ok(s, out, n_frames)) {
-    int e = pqmf::fast16_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, flags, st);
+  if (use_fast(M, L, tables, flags) && pqmf::hankel16_synthesis_ok(s, out, n_frames)) {
+    int e = fast_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   int e = synthesis_direct(s, state_in, out, hk, B, n_frames, M, L, -M, frame_parity, 0, st);
