@@ -75,10 +75,10 @@ struct F16AnalysisParams {
   int num_sms;           // CTAs are launched num_sms at a time: slot of a CTA on its SM = blockIdx.x / num_sms
 };
 
-template <int QN>
+template <int QN, int NXB = 2>
 struct F16AnalysisSmem {
   static constexpr int XS = 32 * (64 + QN);     // floats per x window
-  static constexpr int NXBUF = 3;
+  static constexpr int NXBUF = NXB;
   static constexpr int APLANE = 4 * kF16LboA;   // one fp16 plane of the A operand [128 x 32]
   static constexpr int BCAT = 4 * 512;          // B = [c1 | c2]: N = 32 rows x K = 32 fp16, 4 K-chunks x (32 rows x 16 B)
   static constexpr int BRES = 4 * 256;          // B = 2^-11 c1 : N = 16 rows x K = 32 fp16
@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
   const int pp = lane & 15;              // phase pair: phases 2pp, 2pp+1
   const int mg = warp * 2 + (lane >> 4);  // m-group: frame pairs [8 mg, 8 mg + 8)
   const int phi = 2 * pp;
-  constexpr int mma_warp = 0, kTmaWarp = 3;
 
   // ---- one-time setup: barriers, TMEM, B operands in UMMA K-major layout, taps in registers ----
   if (tid == 0) {
@@ -229,12 +228,15 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
   const long first = blockIdx.x, stride = gridDim.x;
   unsigned cur_b = blockIdx.x / tpr, cur_c = blockIdx.x % tpr;  // tile being folded
   unsigned nxt_b = cur_b, nxt_c = cur_c;                        // tile being staged (NXBUF iterations ahead)
+  constexpr int mma_warp = 0, kTmaWarp = 3;  // (rotating the issuer roles over warps / CTAs measured no gain)
   if (warp == kTmaWarp) {  // prologue: stage the first NXBUF tiles
     for (int i = 0; i < S::NXBUF; ++i) {
       const long tile = first + (long)i * stride;
       if (tile < p.n_tiles) stage_tile(nxt_b, nxt_c, i);
       advance(nxt_b, nxt_c);
     }
+  } else {
+    for (int i = 0; i < S::NXBUF; ++i) advance(nxt_b, nxt_c);
   }
 
   unsigned it = 0;
@@ -269,9 +271,9 @@ __global__ void __launch_bounds__(kF16Threads, 4) f16_analysis_kernel(F16Analysi
         ptx::mbar_wait(&xempty[buf], xphase);
         stage_tile(nxt_b, nxt_c, buf);
       }
-      advance(nxt_b, nxt_c);
       __syncwarp();
     }
+    advance(nxt_b, nxt_c);  // every warp tracks the staged tile (the issuer role may rotate)
     // the previous tile's MMAs must have finished reading the A planes before they are overwritten
     if (it > 0) ptx::mbar_wait(mma_bar, (uint32_t)((it - 1) & 1));
     // ---------------- two-term fp16 split, stored as the UMMA A operand (h1 plane, h2 plane) ----------------
