@@ -281,7 +281,7 @@ def run_gpu(args):
                    "l2": "per-step working set 805 MB per GPU (x, sub-bands, out) exceeds the 126 MB L2; no flush needed",
                    "round_trip_snr_db": round(snr_db, 2)},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": BATCH * N_SAMPLES * 4, "d2h_bytes_per_step": BATCH * N_SAMPLES * 4,
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 4, "d2h_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 4,
                 "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "api": "pqmf_roundtrip_host_f32 (C ABI, pinned host buffers, 16 MiB row chunks on 4 streams)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
