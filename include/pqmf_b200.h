@@ -42,6 +42,7 @@ extern "C" {
 #define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
                               * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
 
+#define PQMF_FLAG_FOLD 4u    /* n_band 16 only: force the fold + modulation kernels (the streaming kernels) offline too */
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* from pqmf_build_tables_f32 */
 
 typedef void* pqmf_stream_t; /* cudaStream_t */

@@ -1,0 +1,62 @@
+// Timeline of the Hankel-4 analysis kernel: clock64 stamps of every warp of CTA 0 at the phase boundaries of each tile
+// (hankel4.cuh, H4_STAMP) -> where does a tile's ~5700 cycles go?
+#define PQMF_H4_TRACE 1
+#include <cstdio>
+#include <vector>
+#include "../hankel4.cuh"
+using namespace pqmf;
+int main(int argc, char**) {
+  const int B = 64; const long T = 1 << 20, F = T / 16;
+  float *x, *y; uint16_t* bank; long long* tr;
+  cudaMalloc(&x, (size_t)B * T * 4); cudaMalloc(&y, (size_t)B * T * 4); cudaMalloc(&bank, 27 * 4096); cudaMalloc(&tr, (64 * 64 + 512) * 8);
+  cudaMemset(x, 0, (size_t)B * T * 4); cudaMemset(bank, 0, 27 * 4096); cudaMemset(tr, 0, 64 * 64 * 8);
+  if (argc > 1) {   // random signal and bank instead of zeros (does the data change the timing?)
+    std::vector<float> hx(1 << 22), hk(16 * 512);
+    srand(3);
+    for (auto& v : hx) v = (float)rand() / RAND_MAX - 0.5f;
+    for (auto& v : hk) v = ((float)rand() / RAND_MAX - 0.5f) * 0.05f;
+    for (size_t o = 0; o < (size_t)B * T; o += hx.size()) cudaMemcpy(x + o, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice);
+    std::vector<uint16_t> ia(27 * 2048), is(27 * 2048);
+    hankel4_build_banks(hk.data(), 64, 384, ia.data(), is.data());
+    cudaMemcpy(bank, ia.data(), ia.size() * 2, cudaMemcpyHostToDevice);
+  }
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  H4AnalysisParams p{};
+  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr;
+  for (int rep = 0; rep < 3; ++rep) {
+    int rc = h4_launch_analysis<64, 384>(p, B, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc || e) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
+  }
+  cudaEventRecord(e0);
+  for (int rep = 0; rep < 20; ++rep) h4_launch_analysis<64, 384>(p, B, 0);
+  cudaEventRecord(e1); cudaDeviceSynchronize();
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  printf("%s data: %.1f us per launch (20 back to back)\n", argc > 1 ? "random" : "zero", ms * 50.f);
+  std::vector<long long> h(64 * 64 + 512);
+  cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost);
+  {
+    long long cmin = 1LL << 60, cmax = 0, nmin = 1LL << 60, nmax = 0;
+    for (int i = 0; i < 148; ++i) {
+      const long long c = h[64 * 64 + 2 * i], n = h[64 * 64 + 2 * i + 1];
+      cmin = c < cmin ? c : cmin; cmax = c > cmax ? c : cmax; nmin = n < nmin ? n : nmin; nmax = n > nmax ? n : nmax;
+    }
+    printf("per-CTA lifetime: %lld..%lld cycles, %lld..%lld ns -> SM clock %.0f MHz (CTA 0: %lld cycles / %lld ns)\n", cmin, cmax, nmin, nmax,
+           1e3 * (double)cmax / (double)nmax, h[64 * 64], h[64 * 64 + 1]);
+  }
+  const long long t00 = h[(0 * 8 + 1) * 8 + 0];
+  printf("warp 1 (MMA warp) and warp 5; cycles relative to the first stamp\n");
+  printf("it |  start   conv   loads  mma_issued  mma(it-1)_done  epi_done | period\n");
+  long long prev = t00;
+  for (int it = 0; it < 56; ++it) {
+    for (int w : {1, 5}) {
+      long long* r = &h[((size_t)it * 8 + w) * 8];
+      if (!r[0]) continue;
+      printf("%2d w%d %8lld %6lld %6lld %6lld %10lld %10lld", it, w, r[0] - t00, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] ? r[4] - r[3] : 0, r[4] ? r[5] - r[4] : 0);
+      if (w == 1) { printf(" | %lld", r[0] - prev); prev = r[0]; }
+      printf("\n");
+    }
+    if (it == 12) it = 40;
+  }
+  return 0;
+}

@@ -1,0 +1,529 @@
+// n_band = 16 PQMF, offline fast path: the direct form as an implicit-Hankel GEMM with FOUR frames per operand row.
+//
+// hankel16.cuh shows that a strided signal can be fed to tcgen05.mma without im2col (one frame = 32 B = the SWIZZLE_32B row
+// pitch), but there every 16 taps cost a full shared-memory read of the 128-row A tile (96 B/sample: smem-bound at ~40 % of
+// the HBM roofline).  Here one A row holds FOUR frames (64 samples = 128 B in fp16 = the SWIZZLE_128B row pitch) and the
+// bank is replicated at the four frame offsets along N:
+//   analysis : D[i, (delta, k)] = sum_kappa X[64 i + kappa] * hk[k, kappa - 16 delta]      = y[k, frame 4 i + delta]
+//   synthesis: D[i, (delta, p)] = sum_(e,k) S^T[4 i + o - e, k] * 16 hk[k, 16 (e + delta) + p] = out[16 (4 i + delta) + p]
+// so one 128-row MMA (N = 128) yields 512 frames, each signal byte is read from shared memory 4x less often
+// (~46 B/sample), and the tensor pipe (27 x [N=128 + N=64] MMAs = 2592 cycles per 8192 samples) sits just under the HBM
+// time of the same tile (2664 cycles at 6.55 TB/s, 1.8 GHz).  K-step s reads rows starting at byte 128 (s / 4) + 32 (s % 4).
+// Precision: the same two-term fp16 split as hankel16.cuh (exact in hk up to 2^-22), columns 0-63 main term, 64-127 the
+// c2 correction; the second pass (h2) uses only the c1 half (N = 64).
+// CUDA cores only convert fp32 -> 2 x fp16 (swizzled STS) and drain TMEM: ~8 thread-instructions per sample.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "hankel16.cuh"
+#include "ptx.cuh"
+
+namespace pqmf {
+
+constexpr int kH4Workers = 256;                 // convert + drain warps
+constexpr int kH4Threads = kH4Workers + 32;     // + one warp that only issues tcgen05.mma (the issue queue blocks the issuing thread)
+constexpr int kH4Rows = 128;             // A rows per tile
+constexpr int kH4Frames = 4 * kH4Rows;   // 512 frames = 8192 samples per tile
+
+// K-major SWIZZLE_128B descriptor: rows 128 B apart, 8-row groups 1024 B apart, 16-byte chunk index ^= address bits 7-9
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t sw128_offset(uint32_t byte_lin) { return byte_lin ^ (((byte_lin >> 7) & 7u) << 4); }
+
+template <int KT>
+struct H4Geometry {
+  static constexpr int KS = KT / 16 + 3;                        // K-steps: taps + the three extra frame offsets
+  static constexpr int ROWS = kH4Rows + ((KS - 1) >> 2) + 1;    // 128-byte rows of one plane
+  static constexpr int PLANE = ((ROWS * 128 + 1023) / 1024) * 1024;
+  static constexpr int BANK = KS * 2 * 128 * 16;                // [2 KS chunks][128 rows][16 B]
+  static constexpr int OFF_BANK = 0;
+  static constexpr int OFF_P = OFF_BANK + BANK;                 // [2 buffers][h1, h2]
+  static constexpr int OFF_BAR = OFF_P + 4 * PLANE;
+  static constexpr int BYTES = OFF_BAR + 128;
+};
+
+// one elected lane: 2 KS MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T
+template <int KS>
+__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr) {
+  const uint64_t da1 = umma_desc_sw128(plane1_addr), da2 = umma_desc_sw128(plane2_addr);
+  const uint64_t db = ptx::umma_desc(bank_addr, 2048, 128);
+  constexpr uint32_t idesc128 = ptx::umma_idesc_f16(128, 128), idesc64 = ptx::umma_idesc_f16(128, 64);
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+    ptx::umma_f16(d_tmem, da1 + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db + (uint64_t)(256 * s), idesc128, s != 0);
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+    ptx::umma_f16(d_tmem, da2 + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db + (uint64_t)(256 * s), idesc64, true);
+}
+
+// =============================================================================================
+// analysis
+// =============================================================================================
+struct H4AnalysisParams {
+  const float* x;        // [B, T]
+  float* y;              // [B, 16, F]
+  const uint16_t* bank;  // fp16 image [2 KS][128][8]
+  long T, F;
+  int off;               // 256 (offline only: streaming blocks are far smaller than a tile)
+  int parity;
+  long tiles_per_row, n_tiles;
+#ifdef PQMF_H4_TRACE
+  long long* trace;      // [iterations][8 warps][8] clock64 stamps of CTA 0 (experiments/trace_h4.cu)
+#endif
+};
+
+#ifdef PQMF_H4_TRACE
+#define H4_STAMP(k) do { if (blockIdx.x == 0 && (tid & 31) == 0 && it < 64) p.trace[((size_t)it * 8 + warp) * 8 + (k)] = clock64(); } while (0)
+#else
+#define H4_STAMP(k) do { } while (0)
+#endif
+
+template <int JLO, int KT>
+__global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisParams p) {
+  using G = H4Geometry<KT>;
+  constexpr int KS = G::KS;
+  constexpr int NQ = (G::ROWS * 16 + kH4Workers - 1) / kH4Workers;  // float4 loads per thread per tile (row = 16 quads)
+  extern __shared__ __align__(1024) unsigned char h4_smem[];
+  unsigned char* smem = h4_smem;
+  unsigned char* bank = smem + G::OFF_BANK;
+  unsigned char* planes = smem + G::OFF_P;
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);  // [2]
+  uint64_t* mma_bar = pfull + 2;                                     // [2]
+  uint64_t* bankfull = mma_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bankfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int kMmaWarp = kH4Workers / 32;
+  if (tid == 0) {
+    ptx::mbar_init(&pfull[0], kH4Workers);
+    ptx::mbar_init(&pfull[1], kH4Workers);
+    ptx::mbar_init(&mma_bar[0], 1);
+    ptx::mbar_init(&mma_bar[1], 1);
+    ptx::mbar_init(bankfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(bankfull, G::BANK);
+    ptx::bulk_g2s(bank, p.bank, G::BANK, bankfull);
+  }
+
+  const unsigned tpr = (unsigned)p.tiles_per_row;
+  const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
+  unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
+  const unsigned n_iter = (unsigned)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+#ifdef PQMF_H4_TRACE
+  long long cta_c0 = clock64(), cta_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
+#endif
+
+  // this thread's share of the fp32 window of one tile (prefetched one tile ahead, straight from global memory)
+  float4 xr[NQ];
+  auto load_window = [&](unsigned bb, unsigned cc) {
+    const long s0 = (long)cc * (kH4Frames * 16) + JLO - p.off;
+    const float* xrow = p.x + (size_t)bb * p.T;
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) {
+      const int q = tid + kH4Workers * r;
+      const long s = s0 + 4L * q;
+      xr[r] = (q < G::ROWS * 16 && s >= 0 && s < p.T) ? __ldcs(reinterpret_cast<const float4*>(xrow + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // D (TMEM) -> y: thread (row i, band half hb) owns frames 4 i .. 4 i + 3 of bands 8 hb .. 8 hb + 7: one float4 per band
+  auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
+    const int i = tid & 127, hb = tid >> 7;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 8 * hb);
+    const long n = (long)cc * kH4Frames + 4 * i;
+    const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
+    float v[4][8];
+#pragma unroll
+    for (int dl = 0; dl < 4; ++dl) {
+      uint32_t r0[8], r1[8];
+      ptx::tmem_ld8(taddr + dl * 16, r0);
+      ptx::tmem_ld8(taddr + 64 + dl * 16, r1);
+      ptx::tmem_ld_wait();
+      // sigma(k, n): odd bands flip on even frames; tiles and 4 i are even, so the frame parity is that of dl (+ p.parity)
+      const uint32_t flip = (((dl + p.parity) & 1) == 0) ? 0x80000000u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const float t = (__uint_as_float(r0[kk]) + __uint_as_float(r1[kk])) * scale;
+        v[dl][kk] = __uint_as_float(__float_as_uint(t) ^ ((kk & 1) ? flip : 0u));
+      }
+    }
+    float* yp = p.y + ((size_t)bb * 16 + 8 * hb) * p.F + n;
+    if (n + 3 < p.F && (p.F & 3) == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) __stcs(reinterpret_cast<float4*>(yp + (size_t)kk * p.F), make_float4(v[0][kk], v[1][kk], v[2][kk], v[3][kk]));
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+        for (int dl = 0; dl < 4; ++dl)
+          if (n + dl < p.F) yp[(size_t)kk * p.F + dl] = v[dl][kk];
+    }
+  };
+
+  const uint32_t bank_addr = ptx::smem_u32(bank), plane_addr = ptx::smem_u32(planes);
+  if (warp == kMmaWarp) {
+    // ---- issuer warp: tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps the issuing
+    //      thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
+    ptx::mbar_wait(bankfull, 0);
+    for (unsigned it = 0; it < n_iter; ++it) {
+      const int pb = (int)(it & 1);
+      ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one_sync()) {
+        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr);
+        ptx::umma_commit(&mma_bar[pb]);
+      }
+      __syncwarp();
+    }
+  } else {
+  load_window(b, c);
+  unsigned prev_b = 0, prev_c = 0;
+  for (unsigned it = 0; it < n_iter; ++it) {
+    const int pb = (int)(it & 1);
+    H4_STAMP(0);
+    // ---- fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples).  planes[pb] were last read by the MMAs of
+    //      tile it-2, whose completion this thread observed before draining tile it-2.
+    {
+      unsigned char* p1 = planes + (2 * pb) * G::PLANE;
+      unsigned char* p2 = p1 + G::PLANE;
+#pragma unroll
+      for (int r = 0; r < NQ; ++r) {
+        const int q = tid + kH4Workers * r;
+        if (q < G::ROWS * 16) {
+          uint2 a, bq;
+          split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
+          split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
+          const uint32_t o = sw128_offset((uint32_t)q * 8u);
+          *reinterpret_cast<uint2*>(p1 + o) = a;
+          *reinterpret_cast<uint2*>(p2 + o) = bq;
+        }
+      }
+    }
+    H4_STAMP(1);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&pfull[pb]);
+    // prefetch the next tile's window (consumed at the top of the next iteration)
+    unsigned nb = b + step_b, nc = c + step_c;
+    if (nc >= tpr) {
+      nc -= tpr;
+      ++nb;
+    }
+    if (it + 1 < n_iter) load_window(nb, nc);
+    H4_STAMP(2);
+    H4_STAMP(3);
+    if (it > 0) {
+      ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      ptx::tc_fence_after();
+      H4_STAMP(4);
+      epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+    }
+    H4_STAMP(5);
+    prev_b = b;
+    prev_c = c;
+    b = nb;
+    c = nc;
+  }
+  ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+  ptx::tc_fence_after();
+  epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+  }  // workers
+  ptx::tc_fence_before();
+  __syncthreads();
+#ifdef PQMF_H4_TRACE
+  if (tid == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.trace[64 * 64 + 2 * blockIdx.x] = clock64() - cta_c0;
+    p.trace[64 * 64 + 2 * blockIdx.x + 1] = t1 - cta_t0;
+  }
+#endif
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+// =============================================================================================
+// synthesis
+// =============================================================================================
+struct H4SynthesisParams {
+  const float* s;        // [B, 16, F]
+  float* out;            // [B, 16 F]
+  const uint16_t* bank;
+  long F;
+  int o;                 // off2 / 16: 16 (PQMF.inverse) or 15 (CachedPQMF.inverse)
+  int parity;
+  long tiles_per_row, n_tiles;
+};
+
+template <int JLO, int KT>
+__global__ void __launch_bounds__(kH4Threads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
+  using G = H4Geometry<KT>;
+  constexpr int KS = G::KS;
+  constexpr int EHI = (JLO + KT) / 16 - 1;        // largest frame lag with a non-zero tap
+  constexpr int MF = 4 * (kH4Rows - 1) + KS;      // sub-band frames a tile reads
+  constexpr int NR = (MF + kH4Workers - 1) / kH4Workers;
+  extern __shared__ __align__(1024) unsigned char h4s_smem[];
+  unsigned char* smem = h4s_smem;
+  unsigned char* bank = smem + G::OFF_BANK;
+  unsigned char* planes = smem + G::OFF_P;
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
+  uint64_t* mma_bar = pfull + 2;
+  uint64_t* bankfull = mma_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bankfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int kMmaWarp = kH4Workers / 32;
+  if (tid == 0) {
+    ptx::mbar_init(&pfull[0], kH4Workers);
+    ptx::mbar_init(&pfull[1], kH4Workers);
+    ptx::mbar_init(&mma_bar[0], 1);
+    ptx::mbar_init(&mma_bar[1], 1);
+    ptx::mbar_init(bankfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(bankfull, G::BANK);
+    ptx::bulk_g2s(bank, p.bank, G::BANK, bankfull);
+  }
+
+  const unsigned tpr = (unsigned)p.tiles_per_row;
+  const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
+  unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
+  const unsigned n_iter = (unsigned)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  // plane frame m <-> sub-band frame n = 512 c + o - EHI + m; thread t owns frames t, t + 256, t + 512 (prefetched)
+  float v[NR][16];
+  auto load_frames = [&](unsigned bb, unsigned cc) {
+    const float* sb = p.s + (size_t)bb * 16 * p.F;
+    const long n0 = (long)cc * kH4Frames + p.o - EHI;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int m = tid + kH4Workers * r;
+      const long n = n0 + m;
+      if (m < MF && n >= 0 && n < p.F) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[r][k] = __ldcs(sb + (size_t)k * p.F + n);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[r][k] = 0.f;
+      }
+    }
+  };
+  // D (TMEM) -> out: thread (row i, half hb) owns output frames 4 i + 2 hb and 4 i + 2 hb + 1: 32 consecutive samples
+  auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
+    const int i = tid & 127, hb = tid >> 7;
+    const long f = (long)cc * kH4Frames + 4 * i + 2 * hb;
+    float* op = p.out + ((size_t)bb * p.F + f) * 16;
+    const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd) {
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + (2 * hb + dd) * 16);
+      uint32_t r0[16], r1[16];
+      ptx::tmem_ld16(taddr, r0);
+      ptx::tmem_ld16(taddr + 64, r1);
+      ptx::tmem_ld_wait();
+      if (f + dd < p.F) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float4 w;
+          w.x = (__uint_as_float(r0[4 * c4 + 0]) + __uint_as_float(r1[4 * c4 + 0])) * scale;
+          w.y = (__uint_as_float(r0[4 * c4 + 1]) + __uint_as_float(r1[4 * c4 + 1])) * scale;
+          w.z = (__uint_as_float(r0[4 * c4 + 2]) + __uint_as_float(r1[4 * c4 + 2])) * scale;
+          w.w = (__uint_as_float(r0[4 * c4 + 3]) + __uint_as_float(r1[4 * c4 + 3])) * scale;
+          __stcs(reinterpret_cast<float4*>(op + dd * 16 + c4 * 4), w);
+        }
+      }
+    }
+  };
+
+  const uint32_t bank_addr = ptx::smem_u32(bank), plane_addr = ptx::smem_u32(planes);
+  if (warp == kMmaWarp) {
+    // ---- issuer warp: tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps the issuing
+    //      thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
+    ptx::mbar_wait(bankfull, 0);
+    for (unsigned it = 0; it < n_iter; ++it) {
+      const int pb = (int)(it & 1);
+      ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one_sync()) {
+        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr);
+        ptx::umma_commit(&mma_bar[pb]);
+      }
+      __syncwarp();
+    }
+  } else {
+  load_frames(b, c);
+  unsigned prev_b = 0, prev_c = 0;
+  for (unsigned it = 0; it < n_iter; ++it) {
+    const int pb = (int)(it & 1);
+    {
+      unsigned char* p1 = planes + (2 * pb) * G::PLANE;
+      const long n0 = (long)c * kH4Frames + p.o - EHI;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int m = tid + kH4Workers * r;
+        if (m < MF) {
+          if (((n0 + m + p.parity) & 1) == 0) {
+#pragma unroll
+            for (int k = 1; k < 16; k += 2) v[r][k] = -v[r][k];
+          }
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint4 h1, h2;
+            split2_f16(v[r][8 * ch + 0], v[r][8 * ch + 1], h1.x, h2.x);
+            split2_f16(v[r][8 * ch + 2], v[r][8 * ch + 3], h1.y, h2.y);
+            split2_f16(v[r][8 * ch + 4], v[r][8 * ch + 5], h1.z, h2.z);
+            split2_f16(v[r][8 * ch + 6], v[r][8 * ch + 7], h1.w, h2.w);
+            const uint32_t o = sw128_offset((uint32_t)m * 32u + 16u * ch);
+            *reinterpret_cast<uint4*>(p1 + o) = h1;
+            *reinterpret_cast<uint4*>(p1 + G::PLANE + o) = h2;
+          }
+        }
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&pfull[pb]);
+    unsigned nb = b + step_b, nc = c + step_c;
+    if (nc >= tpr) {
+      nc -= tpr;
+      ++nb;
+    }
+    if (it + 1 < n_iter) load_frames(nb, nc);
+    if (it > 0) {
+      ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      ptx::tc_fence_after();
+      epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+    }
+    prev_b = b;
+    prev_c = c;
+    b = nb;
+    c = nc;
+  }
+  ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+  ptx::tc_fence_after();
+  epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+  }  // workers
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+template <typename Kern>
+inline int h4_configure(Kern kern, int bytes, bool (&configured)[64], int& sm_count_out) {
+  static int sm_count[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (sm_count[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sm_count[dev] = n > 0 ? n : 148;
+  }
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    configured[dev] = true;
+  }
+  sm_count_out = sm_count[dev];
+  return 0;
+}
+
+template <int JLO, int KT>
+int h4_launch_analysis(H4AnalysisParams p, int B, cudaStream_t st) {
+  using G = H4Geometry<KT>;
+  auto kern = h4_analysis_kernel<JLO, KT>;
+  static bool configured[64] = {false};
+  int sms = 0;
+  if (int e = h4_configure(kern, G::BYTES, configured, sms)) return e;
+  p.tiles_per_row = (p.F + kH4Frames - 1) / kH4Frames;
+  p.n_tiles = p.tiles_per_row * B;
+  if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
+  long grid = sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, kH4Threads, G::BYTES, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+template <int JLO, int KT>
+int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
+  using G = H4Geometry<KT>;
+  auto kern = h4_synthesis_kernel<JLO, KT>;
+  static bool configured[64] = {false};
+  int sms = 0;
+  if (int e = h4_configure(kern, G::BYTES, configured, sms)) return e;
+  p.tiles_per_row = (p.F + kH4Frames - 1) / kH4Frames;
+  p.n_tiles = p.tiles_per_row * B;
+  if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
+  long grid = sms;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<(unsigned)grid, kH4Threads, G::BYTES, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: bank images, fp16 bits in UMMA K-major no-swizzle layout [chunk of 8 K][128 rows][8],
+// rows = part * 64 + delta * 16 + (band | phase), part 0 = c1, part 1 = c2
+// ---------------------------------------------------------------------------------------------
+inline void hankel4_build_banks(const float* hk /*[16][512]*/, int jlo, int kt, uint16_t* img_analysis, uint16_t* img_synthesis) {
+  auto bits = [](float v) {
+    const __half h = __float2half_rn(v);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+  };
+  const int ks = kt / 16 + 3, kp = 16 * ks;
+  const int dlo = jlo / 16, dhi = (jlo + kt) / 16 - 1;
+  const float sa = (float)(1 << kH16ScaleLog2), ss = 16.f * sa;
+  for (int kc = 0; kc < kp / 8; ++kc)
+    for (int row = 0; row < 128; ++row)
+      for (int e = 0; e < 8; ++e) {
+        const int kap = 8 * kc + e;
+        const int part = row / 64, delta = (row % 64) / 16, q = row % 16;
+        const size_t at = ((size_t)kc * 128 + row) * 8 + e;
+        {  // analysis: K index = tap offset within the (delta-shifted) window, q = band
+          const int j = kap - 16 * delta;
+          const float v = (j >= 0 && j < kt) ? sa * hk[q * 512 + jlo + j] : 0.f;
+          const float c1 = __half2float(__float2half_rn(v));
+          img_analysis[at] = part == 0 ? bits(c1) : bits(v - c1);
+        }
+        {  // synthesis: K index = (step s, band kb): lag e = dhi - s, tap 16 (e + delta) + q, q = output phase
+          const int s2 = kap / 16, kb = kap % 16, d = dhi - s2 + delta;
+          const float v = (d >= dlo && d <= dhi) ? ss * hk[kb * 512 + 16 * d + q] : 0.f;
+          const float c1 = __half2float(__float2half_rn(v));
+          img_synthesis[at] = part == 0 ? bits(c1) : bits(v - c1);
+        }
+      }
+}
+
+}  // namespace pqmf

@@ -16,6 +16,7 @@
 #include "fast16.cuh"
 #include "fast16_synth.cuh"
 #include "hankel16.cuh"
+#include "hankel4.cuh"
 
 namespace {
 
@@ -133,6 +134,26 @@ HostWorkspace g_host_ws[kMaxDevices];
 std::mutex g_host_mutex;
 
 constexpr long kFoldTableFloats = 512 + 2 * 16 * 32;  // [ g | c1 | c2 ] of the fold + modulation path
+constexpr long kH16ImageFloats = 512L * 16;            // one hankel16 bank image (fp16 [KT/8][32][8]), sized for KT = 512
+constexpr long kH4TableOffset = kFoldTableFloats + 2 * kH16ImageFloats;
+constexpr long kH4ImageFloats = 35L * 4096 / 4;        // one hankel4 bank image (fp16 [2 KS][128][8]), sized for KS = 35
+
+// offline n_band 16 default: four-frames-per-row Hankel GEMM (hankel4.cuh) when there are enough 512-frame tiles
+bool use_h4(int B, long F, const float* hist) { return hist == nullptr && (long)B * ((F + 511) / 512) >= 96; }
+int h4_analysis(const float* x, float* y, const float* tables, int B, long T, long F, int off, unsigned flags, cudaStream_t st) {
+  const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
+  pqmf::H4AnalysisParams p{};
+  p.x = x; p.y = y; p.T = T; p.F = F; p.off = off; p.parity = 0;
+  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
+  return trimmed ? pqmf::h4_launch_analysis<64, 384>(p, B, st) : pqmf::h4_launch_analysis<0, 512>(p, B, st);
+}
+int h4_synthesis(const float* s, float* out, const float* tables, int B, long F, int off2, unsigned flags, cudaStream_t st) {
+  const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
+  pqmf::H4SynthesisParams p{};
+  p.s = s; p.out = out; p.F = F; p.o = off2 / 16; p.parity = 0;
+  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
+  return trimmed ? pqmf::h4_launch_synthesis<64, 384>(p, B, st) : pqmf::h4_launch_synthesis<0, 512>(p, B, st);
+}
 
 // n_band 16 fast path: fold + tensor-core modulation (fast16*.cuh), or -- with PQMF_FLAG_EXACT -- the direct form as an
 // implicit-Hankel GEMM on the tensor cores (hankel16.cuh).  flags bits [8,12) = first active tap / 32, [12,17) = taps / 32.
@@ -165,12 +186,16 @@ int exact_tc_synthesis(const float* s, const float* hist, float* out, float* his
 
 int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, const float* tables, int B, long T, long F, int off,
                   int parity, unsigned flags, cudaStream_t st) {
+  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, hist) && ((uintptr_t)y % 16) == 0)
+    return h4_analysis(x, y, tables, B, T, F, off, flags, st);
   if (flags & PQMF_FLAG_EXACT) return exact_tc_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
   return pqmf::fast16_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
 }
 
 int fast_synthesis(const float* s, const float* hist, float* out, float* hist_out, const float* tables, int B, long F, int off2,
                    int parity, unsigned flags, cudaStream_t st) {
+  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, hist) && ((uintptr_t)out % 16) == 0 && off2 % 16 == 0)
+    return h4_synthesis(s, out, tables, B, F, off2, flags, st);
   if (flags & PQMF_FLAG_EXACT) return exact_tc_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
   return pqmf::fast16_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
 }
@@ -199,7 +224,7 @@ unsigned long long pqmf_launch_count(void) { return g_launches.load(); }
 
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags) { return use_fast(M, L, tables, flags) ? 1 : 0; }
 
-long pqmf_tables_numel(int M, int L) { return pqmf::hankel16_supported(M, L) ? kFoldTableFloats + 2L * L * 16 : 0; }
+long pqmf_tables_numel(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4TableOffset + 2L * kH4ImageFloats : 0; }
 
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
                           double* residual, unsigned* fast_flags) {
@@ -252,6 +277,9 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   const int jlo = trimmed ? 64 : 0, kt = trimmed ? 384 : 512;
   uint16_t* img = reinterpret_cast<uint16_t*>(tables_host + kFoldTableFloats);
   pqmf::hankel16_build_banks(hk_host, jlo, kt, img, img + (size_t)kt * 32);
+  // ---- part 3: the same bank replicated at four frame offsets for the offline default path (hankel4.cuh)
+  uint16_t* img4 = reinterpret_cast<uint16_t*>(tables_host + kH4TableOffset);
+  pqmf::hankel4_build_banks(hk_host, jlo, kt, img4, img4 + 2 * kH4ImageFloats);
   if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32);
   return PQMF_OK;
 }

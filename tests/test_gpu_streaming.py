@@ -80,7 +80,7 @@ def test_config3_many_streams(pq):
     x = (0.5 * torch.randn(streams, 1, block * n_blocks, device="cuda")).clamp_(-1, 1)
     y_s, out_s = _run_stream(mod, x, block)
     xz = torch.cat([torch.zeros(streams, 1, 256, device="cuda"), x], dim=-1)
-    assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 2e-6
+    assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 5e-6  # streamed (fold kernels) vs offline (Hankel GEMM)
     lat = mod.cumulative_delay
     err = out_s[..., lat:] - x[..., :-lat]
     snr = 10 * torch.log10((x[..., :-lat] ** 2).sum() / (err ** 2).sum())

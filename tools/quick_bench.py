@@ -9,8 +9,11 @@ def timeit(fn, n=10, warm=3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts = []
+    inner = 6   # back-to-back launches per timed interval, so host launch latency hides behind the previous kernel
     for _ in range(n):
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        fn(); e0.record()
+        for _ in range(inner): fn()
+        e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / inner)
     ts.sort()
     return ts[0], ts[len(ts)//2]
 
