@@ -28,11 +28,20 @@ int main(int argc, char**) {
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
   }
+  const bool synth = argc > 2;
+  H4SynthesisParams q{};
+  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr;
+  if (synth) {
+    cudaMemset(tr, 0, 64 * 64 * 8);
+    h4_launch_synthesis<64, 384>(q, B, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e) { printf("synthesis cuda=%s\n", cudaGetErrorString(e)); return 1; }
+  }
   cudaEventRecord(e0);
-  for (int rep = 0; rep < 20; ++rep) h4_launch_analysis<64, 384>(p, B, 0);
+  for (int rep = 0; rep < 20; ++rep) { if (synth) h4_launch_synthesis<64, 384>(q, B, 0); else h4_launch_analysis<64, 384>(p, B, 0); }
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-  printf("%s data: %.1f us per launch (20 back to back)\n", argc > 1 ? "random" : "zero", ms * 50.f);
+  printf("%s %s data: %.1f us per launch (20 back to back)\n", synth ? "synthesis" : "analysis", argc > 1 ? "random" : "zero", ms * 50.f);
   std::vector<long long> h(64 * 64 + 512);
   cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost);
   {

@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t byte_lin) { return byt
 template <int KT>
 struct H4Geometry {
   static constexpr int KS = KT / 16 + 3;                        // K-steps: taps + the three extra frame offsets
-  static constexpr int ROWS = kH4Rows + ((KS - 1) >> 2) + 1;    // 128-byte rows of one plane
+  static constexpr int ROWS = kH4Rows + ((KS - 1) >> 2) + 1;    // 128-byte rows of one plane (covers the synthesis pad <= 3 too)
   static constexpr int PLANE = ((ROWS * 128 + 1023) / 1024) * 1024;
   static constexpr int BANK = KS * 2 * 128 * 16;                // [2 KS chunks][128 rows][16 B]
   static constexpr int OFF_BANK = 0;
@@ -54,16 +54,16 @@ struct H4Geometry {
 
 // one elected lane: 2 KS MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T
 template <int KS>
-__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr) {
+__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int pad = 0) {
   const uint64_t da1 = umma_desc_sw128(plane1_addr), da2 = umma_desc_sw128(plane2_addr);
   const uint64_t db = ptx::umma_desc(bank_addr, 2048, 128);
   constexpr uint32_t idesc128 = ptx::umma_idesc_f16(128, 128), idesc64 = ptx::umma_idesc_f16(128, 64);
 #pragma unroll
   for (int s = 0; s < KS; ++s)
-    ptx::umma_f16(d_tmem, da1 + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db + (uint64_t)(256 * s), idesc128, s != 0);
+    ptx::umma_f16(d_tmem, da1 + (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)), db + (uint64_t)(256 * s), idesc128, s != 0);
 #pragma unroll
   for (int s = 0; s < KS; ++s)
-    ptx::umma_f16(d_tmem, da2 + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db + (uint64_t)(256 * s), idesc64, true);
+    ptx::umma_f16(d_tmem, da2 + (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)), db + (uint64_t)(256 * s), idesc64, true);
 }
 
 // =============================================================================================
@@ -272,15 +272,20 @@ struct H4SynthesisParams {
   int o;                 // off2 / 16: 16 (PQMF.inverse) or 15 (CachedPQMF.inverse)
   int parity;
   long tiles_per_row, n_tiles;
+#ifdef PQMF_H4_TRACE
+  long long* trace;
+#endif
 };
 
+constexpr int kH4SynWorkers = 288;                    // nine worker warps: 2 x ROWS (<= 274) load/convert items, one per thread
+constexpr int kH4SynThreads = kH4SynWorkers + 32;     // + the issuer warp
+
 template <int JLO, int KT>
-__global__ void __launch_bounds__(kH4Threads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
+__global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
   using G = H4Geometry<KT>;
   constexpr int KS = G::KS;
   constexpr int EHI = (JLO + KT) / 16 - 1;        // largest frame lag with a non-zero tap
-  constexpr int MF = 4 * (kH4Rows - 1) + KS;      // sub-band frames a tile reads
-  constexpr int NR = (MF + kH4Workers - 1) / kH4Workers;
+  static_assert(2 * G::ROWS <= kH4SynWorkers, "one (frame quad, band half) item per worker thread");
   extern __shared__ __align__(1024) unsigned char h4s_smem[];
   unsigned char* smem = h4s_smem;
   unsigned char* bank = smem + G::OFF_BANK;
@@ -291,10 +296,10 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_synthesis_kernel(H4Synthesis
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bankfull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int kMmaWarp = kH4Workers / 32;
+  constexpr int kMmaWarp = kH4SynWorkers / 32;
   if (tid == 0) {
-    ptx::mbar_init(&pfull[0], kH4Workers);
-    ptx::mbar_init(&pfull[1], kH4Workers);
+    ptx::mbar_init(&pfull[0], kH4SynWorkers);
+    ptx::mbar_init(&pfull[1], kH4SynWorkers);
     ptx::mbar_init(&mma_bar[0], 1);
     ptx::mbar_init(&mma_bar[1], 1);
     ptx::mbar_init(bankfull, 1);
@@ -318,118 +323,139 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_synthesis_kernel(H4Synthesis
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
   const unsigned n_iter = (unsigned)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  // plane frame m <-> sub-band frame n = 512 c + o - EHI + m; thread t owns frames t, t + 256, t + 512 (prefetched)
-  float v[NR][16];
-  auto load_frames = [&](unsigned bb, unsigned cc) {
-    const float* sb = p.s + (size_t)bb * 16 * p.F;
-    const long n0 = (long)cc * kH4Frames + p.o - EHI;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int m = tid + kH4Workers * r;
-      const long n = n0 + m;
-      if (m < MF && n >= 0 && n < p.F) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[r][k] = __ldcs(sb + (size_t)k * p.F + n);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[r][k] = 0.f;
-      }
-    }
-  };
-  // D (TMEM) -> out: thread (row i, half hb) owns output frames 4 i + 2 hb and 4 i + 2 hb + 1: 32 consecutive samples
-  auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
-    const int i = tid & 127, hb = tid >> 7;
-    const long f = (long)cc * kH4Frames + 4 * i + 2 * hb;
-    float* op = p.out + ((size_t)bb * p.F + f) * 16;
-    const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
-#pragma unroll
-    for (int dd = 0; dd < 2; ++dd) {
-      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + (2 * hb + dd) * 16);
-      uint32_t r0[16], r1[16];
-      ptx::tmem_ld16(taddr, r0);
-      ptx::tmem_ld16(taddr + 64, r1);
-      ptx::tmem_ld_wait();
-      if (f + dd < p.F) {
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          float4 w;
-          w.x = (__uint_as_float(r0[4 * c4 + 0]) + __uint_as_float(r1[4 * c4 + 0])) * scale;
-          w.y = (__uint_as_float(r0[4 * c4 + 1]) + __uint_as_float(r1[4 * c4 + 1])) * scale;
-          w.z = (__uint_as_float(r0[4 * c4 + 2]) + __uint_as_float(r1[4 * c4 + 2])) * scale;
-          w.w = (__uint_as_float(r0[4 * c4 + 3]) + __uint_as_float(r1[4 * c4 + 3])) * scale;
-          __stcs(reinterpret_cast<float4*>(op + dd * 16 + c4 * 4), w);
-        }
-      }
-    }
-  };
-
+  // plane frame m <-> sub-band frame n = 512 c + (o - EHI - pad) + m, pad = (o - EHI) mod 4, so that frame quads are
+  // 16-byte aligned in global memory; K-step s of row i then reads plane frame 4 i + s + pad.
+  const int pad = (p.o - EHI) & 3;
+  const int nbase = p.o - EHI - pad;              // multiple of 4 (may be negative)
   const uint32_t bank_addr = ptx::smem_u32(bank), plane_addr = ptx::smem_u32(planes);
   if (warp == kMmaWarp) {
-    // ---- issuer warp: tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps the issuing
-    //      thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
+    // ---- issuer warp (see the analysis kernel)
     ptx::mbar_wait(bankfull, 0);
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr);
+        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, pad);
         ptx::umma_commit(&mma_bar[pb]);
       }
       __syncwarp();
     }
   } else {
-  load_frames(b, c);
-  unsigned prev_b = 0, prev_c = 0;
-  for (unsigned it = 0; it < n_iter; ++it) {
-    const int pb = (int)(it & 1);
-    {
-      unsigned char* p1 = planes + (2 * pb) * G::PLANE;
-      const long n0 = (long)c * kH4Frames + p.o - EHI;
+    // ---- workers.  Item (m4, ch): frames 4 m4 .. 4 m4 + 3 of bands 8 ch .. 8 ch + 7 = eight float4 loads (prefetched one
+    //      tile ahead) -> four 16-byte chunks per fp16 plane.  ch-major thread order keeps a quarter-warp on eight
+    //      consecutive rows, whose SWIZZLE_128B images of one chunk column hit eight different bank groups.
+    const int ch = tid >= G::ROWS ? 1 : 0, m4 = tid - ch * G::ROWS;
+    const bool has_item = tid < 2 * G::ROWS;
+    float4 v[8];
+    auto load_frames = [&](unsigned bb, unsigned cc) {
+      const long n = (long)cc * kH4Frames + nbase + 4 * m4;
+      const float* sp = p.s + ((size_t)bb * 16 + 8 * ch) * p.F + n;
+      const bool ok = has_item && n >= 0 && n + 3 < p.F;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const int m = tid + kH4Workers * r;
-        if (m < MF) {
-          if (((n0 + m + p.parity) & 1) == 0) {
+      for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? __ldcs(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // D (TMEM) -> out.  Thread (row i, half hb) drains output frames 4 i + 2 hb, + 1 = 32 consecutive samples = four 32-byte
+    // chunks, but rows are 256 B apart: stored like that, every warp store would touch 32 lines.  A 4 x 4 chunk transpose
+    // inside each lane quad (two shuffle stages) leaves lane r with chunk r & 3 of the quad's four rows, so one STG.256
+    // covers eight whole 128-byte lines.
+    auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
+      const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
+      const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
+      uint32_t r0[2][16], r1[2][16];
+      ptx::tmem_ld16(taddr, r0[0]);
+      ptx::tmem_ld16(taddr + 64, r1[0]);
+      ptx::tmem_ld16(taddr + 16, r0[1]);
+      ptx::tmem_ld16(taddr + 80, r1[1]);
+      ptx::tmem_ld_wait();
+      float val[4][8];   // chunk q = 2 dd + c8
 #pragma unroll
-            for (int k = 1; k < 16; k += 2) v[r][k] = -v[r][k];
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) val[q][e] = (__uint_as_float(r0[q >> 1][8 * (q & 1) + e]) + __uint_as_float(r1[q >> 1][8 * (q & 1) + e])) * scale;
+      const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr)   // lanes r, r ^ 1 swap the off-diagonal chunks of (2 pr, 2 pr + 1)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float recv = __shfl_xor_sync(0xffffffffu, b0 ? val[2 * pr][e] : val[2 * pr + 1][e], 1);
+          val[2 * pr + 1][e] = b0 ? val[2 * pr + 1][e] : recv;
+          val[2 * pr][e] = b0 ? recv : val[2 * pr][e];
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)      // lanes r, r ^ 2 swap the off-diagonal chunks of (u, u + 2)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float recv = __shfl_xor_sync(0xffffffffu, b1 ? val[u][e] : val[u + 2][e], 2);
+          val[u + 2][e] = b1 ? val[u + 2][e] : recv;
+          val[u][e] = b1 ? recv : val[u][e];
+        }
+      // slot q now holds chunk (lane & 3) of row (i & ~3) | q
+      const int cq = lane & 3;
+      const long f0 = (long)cc * kH4Frames + 4 * (i & ~3) + 2 * hb + (cq >> 1);
+      float* op = p.out + ((size_t)bb * p.F + f0) * 16 + 8 * (cq & 1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (f0 + 4 * q < p.F) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
+    };
+
+    load_frames(b, c);
+    unsigned prev_b = 0, prev_c = 0;
+    // sigma(k, n): odd bands (odd kk) flip on even global frames; quads start on multiples of 4, so the parity is j's
+    const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
+    for (unsigned it = 0; it < n_iter; ++it) {
+      const int pb = (int)(it & 1);
+      H4_STAMP(0);
+      if (has_item) {
+        unsigned char* p1 = planes + (2 * pb) * G::PLANE;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t fl = (j & 1) ? flip_odd : flip_even;
+          float w[8];
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const float t = j == 0 ? v[kk].x : j == 1 ? v[kk].y : j == 2 ? v[kk].z : v[kk].w;
+            w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
           }
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint4 h1, h2;
-            split2_f16(v[r][8 * ch + 0], v[r][8 * ch + 1], h1.x, h2.x);
-            split2_f16(v[r][8 * ch + 2], v[r][8 * ch + 3], h1.y, h2.y);
-            split2_f16(v[r][8 * ch + 4], v[r][8 * ch + 5], h1.z, h2.z);
-            split2_f16(v[r][8 * ch + 6], v[r][8 * ch + 7], h1.w, h2.w);
-            const uint32_t o = sw128_offset((uint32_t)m * 32u + 16u * ch);
-            *reinterpret_cast<uint4*>(p1 + o) = h1;
-            *reinterpret_cast<uint4*>(p1 + G::PLANE + o) = h2;
-          }
+          uint4 h1, h2;
+          split2_f16(w[0], w[1], h1.x, h2.x);
+          split2_f16(w[2], w[3], h1.y, h2.y);
+          split2_f16(w[4], w[5], h1.z, h2.z);
+          split2_f16(w[6], w[7], h1.w, h2.w);
+          const uint32_t o = sw128_offset((uint32_t)m4 * 128u + 32u * j + 16u * ch);
+          *reinterpret_cast<uint4*>(p1 + o) = h1;
+          *reinterpret_cast<uint4*>(p1 + G::PLANE + o) = h2;
         }
       }
+      H4_STAMP(1);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&pfull[pb]);
+      unsigned nb = b + step_b, nc = c + step_c;
+      if (nc >= tpr) {
+        nc -= tpr;
+        ++nb;
+      }
+      if (it + 1 < n_iter) load_frames(nb, nc);
+      H4_STAMP(2);
+      H4_STAMP(3);
+      if (it > 0) {
+        // every worker waits (planes[pb ^ 1] are rewritten next iteration); the ninth warp has no TMEM rows to drain
+        ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        H4_STAMP(4);
+        if (warp < 8) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+      }
+      H4_STAMP(5);
+      prev_b = b;
+      prev_c = c;
+      b = nb;
+      c = nc;
     }
-    ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    ptx::mbar_arrive(&pfull[pb]);
-    unsigned nb = b + step_b, nc = c + step_c;
-    if (nc >= tpr) {
-      nc -= tpr;
-      ++nb;
-    }
-    if (it + 1 < n_iter) load_frames(nb, nc);
-    if (it > 0) {
-      ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-      ptx::tc_fence_after();
-      epilogue(prev_b, prev_c, (int)((it - 1) & 1));
-    }
-    prev_b = b;
-    prev_c = c;
-    b = nb;
-    c = nc;
-  }
-  ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-  ptx::tc_fence_after();
-  epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+    ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    if (warp < 8) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
   ptx::tc_fence_before();
   __syncthreads();
@@ -487,7 +513,7 @@ int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
   if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
   long grid = sms;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, kH4Threads, G::BYTES, st>>>(p);
+  kern<<<(unsigned)grid, kH4SynThreads, G::BYTES, st>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -194,7 +194,7 @@ int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, 
 
 int fast_synthesis(const float* s, const float* hist, float* out, float* hist_out, const float* tables, int B, long F, int off2,
                    int parity, unsigned flags, cudaStream_t st) {
-  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, hist) && ((uintptr_t)out % 16) == 0 && off2 % 16 == 0)
+  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, hist) && ((uintptr_t)out % 32) == 0 && ((uintptr_t)s % 16) == 0 && (F & 3) == 0 && off2 % 16 == 0)
     return h4_synthesis(s, out, tables, B, F, off2, flags, st);
   if (flags & PQMF_FLAG_EXACT) return exact_tc_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
   return pqmf::fast16_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
