@@ -254,8 +254,8 @@ def run_gpu(args):
     peak, peak_src = measured_peak_gbs()
     algo_bytes = ALGO_BYTES_PER_SAMPLE_PER_DIRECTION * BATCH * N_SAMPLES
     kernels = {
-        "f16_analysis_kernel": {"ms": t_an, "gbs": algo_bytes / (t_an * 1e-3) * 1e-9},
-        "f16_synthesis_kernel": {"ms": t_sy, "gbs": algo_bytes / (t_sy * 1e-3) * 1e-9},
+        "h4_analysis_kernel": {"ms": t_an, "gbs": algo_bytes / (t_an * 1e-3) * 1e-9},
+        "h4_synthesis_kernel": {"ms": t_sy, "gbs": algo_bytes / (t_sy * 1e-3) * 1e-9},
     }
     dominant = max(kernels, key=lambda k: kernels[k]["ms"])
     traffic = recorded_traffic().get(dominant)

@@ -44,6 +44,9 @@ extern "C" {
 
 #define PQMF_FLAG_FOLD 4u    /* n_band 16 only: force the fold + modulation kernels (the streaming kernels) offline too */
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* from pqmf_build_tables_f32 */
+/* from pqmf_build_tables_f32: edge K-steps (analysis, synthesis) of the offline n_band 16 kernels whose fp16 correction
+ * terms are provably below 4e-6 / 9e-6 of max|input| for this bank and are skipped; 0 keeps every term */
+#define PQMF_FLAG_H4_TRIM(ta, ts) (((unsigned)(ta) << 17) | ((unsigned)(ts) << 20))
 
 typedef void* pqmf_stream_t; /* cudaStream_t */
 

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 }
 
 __global__ void __launch_bounds__(256, 1) contention_kernel(const float4* __restrict__ gin, float4* __restrict__ gout, size_t per_cta, long long* cyc, long long* work,
-                                                             int reps, int mode) {
+                                                             int reps, int mode, int n128 = KS, int n64 = KS) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar[2];
   __shared__ uint32_t slot;
@@ -47,10 +47,8 @@ __global__ void __launch_bounds__(256, 1) contention_kernel(const float4* __rest
       }
       if (elect_one_sync()) {
         const uint64_t da = desc_sw128(smem_u32(sm)), db = umma_desc(smem_u32(sm + OFF_BANK), 2048, 128);
-#pragma unroll
-        for (int s = 0; s < KS; ++s) umma_f16(tm + 128 * (r & 1), da + (uint64_t)(2 * s), db + (uint64_t)(256 * s), umma_idesc_f16(128, 128), s != 0);
-#pragma unroll
-        for (int s = 0; s < KS; ++s) umma_f16(tm + 128 * (r & 1), da + (uint64_t)(2 * s), db + (uint64_t)(256 * s), umma_idesc_f16(128, 64), true);
+        for (int s = 0; s < n128; ++s) umma_f16(tm + 128 * (r & 1), da + (uint64_t)(2 * s), db + (uint64_t)(256 * s), umma_idesc_f16(128, 128), s != 0);
+        for (int s = 0; s < n64; ++s) umma_f16(tm + 128 * (r & 1), da + (uint64_t)(2 * s), db + (uint64_t)(256 * s), umma_idesc_f16(128, 64), true);
         umma_commit(&bar[r & 1]);
       }
       __syncwarp();
@@ -119,6 +117,13 @@ int main() {
     if (m & 4) printf(" | LDG %.1f KB", per_group * 4 * 224 * 16 / 1024);
     if (m & 8) printf(" | STG %.1f KB", per_group * 4 * 224 * 16 / 1024);
     printf(" [%s]\n", cudaGetErrorString(e));
+  }
+  const int shapes[][2] = {{27, 0}, {0, 27}, {27, 27}, {19, 27}, {23, 27}, {1, 0}, {0, 1}};
+  for (auto& sh : shapes) {
+    contention_kernel<<<148, 256, SMEM>>>(gin, gout, per_cta, dc, dw, 100, 0, sh[0], sh[1]);
+    cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+    printf("%2d x N=128 + %2d x N=64 per group: %lld cycles\n", sh[0], sh[1], c);
   }
   return 0;
 }

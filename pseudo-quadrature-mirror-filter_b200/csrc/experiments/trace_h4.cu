@@ -5,7 +5,7 @@
 #include <vector>
 #include "../hankel4.cuh"
 using namespace pqmf;
-int main(int argc, char**) {
+int main(int argc, char** argv) {
   const int B = 64; const long T = 1 << 20, F = T / 16;
   float *x, *y; uint16_t* bank; long long* tr;
   cudaMalloc(&x, (size_t)B * T * 4); cudaMalloc(&y, (size_t)B * T * 4); cudaMalloc(&bank, 27 * 4096); cudaMalloc(&tr, (64 * 64 + 512) * 8);
@@ -22,7 +22,7 @@ int main(int argc, char**) {
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   H4AnalysisParams p{};
-  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr;
+  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim = argc > 3 ? atoi(argv[3]) : 0;
   for (int rep = 0; rep < 3; ++rep) {
     int rc = h4_launch_analysis<64, 384>(p, B, 0);
     cudaError_t e = cudaDeviceSynchronize();
@@ -30,7 +30,7 @@ int main(int argc, char**) {
   }
   const bool synth = argc > 2;
   H4SynthesisParams q{};
-  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr;
+  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim = argc > 3 ? atoi(argv[3]) : 0;
   if (synth) {
     cudaMemset(tr, 0, 64 * 64 * 8);
     h4_launch_synthesis<64, 384>(q, B, 0);

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -52,18 +53,22 @@ struct H4Geometry {
   static constexpr int BYTES = OFF_BAR + 128;
 };
 
-// one elected lane: 2 KS MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T
+// one elected lane: the MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T.  The first and last `trim`
+// K-steps carry only the tails of the prototype: there the two correction terms (h1 c2, h2 c1) are below the error budget
+// that pqmf_build_tables_f32 checked against the actual bank, so those steps run h1 c1 alone (N = 64) and no h2 pass.
+// `pad` shifts the A windows by whole frames (synthesis alignment).
 template <int KS>
-__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int pad = 0) {
+__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int pad, int trim) {
   const uint64_t da1 = umma_desc_sw128(plane1_addr), da2 = umma_desc_sw128(plane2_addr);
   const uint64_t db = ptx::umma_desc(bank_addr, 2048, 128);
   constexpr uint32_t idesc128 = ptx::umma_idesc_f16(128, 128), idesc64 = ptx::umma_idesc_f16(128, 64);
-#pragma unroll
-  for (int s = 0; s < KS; ++s)
-    ptx::umma_f16(d_tmem, da1 + (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)), db + (uint64_t)(256 * s), idesc128, s != 0);
-#pragma unroll
-  for (int s = 0; s < KS; ++s)
-    ptx::umma_f16(d_tmem, da2 + (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)), db + (uint64_t)(256 * s), idesc64, true);
+  auto a_step = [&](int s) { return (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)); };  // 128 B per 4 frames, 32 B per frame
+  for (int s = trim; s < KS - trim; ++s) ptx::umma_f16(d_tmem, da1 + a_step(s), db + (uint64_t)(256 * s), idesc128, s != trim);
+  for (int s = 0; s < trim; ++s) {
+    ptx::umma_f16(d_tmem, da1 + a_step(s), db + (uint64_t)(256 * s), idesc64, true);
+    ptx::umma_f16(d_tmem, da1 + a_step(KS - 1 - s), db + (uint64_t)(256 * (KS - 1 - s)), idesc64, true);
+  }
+  for (int s = trim; s < KS - trim; ++s) ptx::umma_f16(d_tmem, da2 + a_step(s), db + (uint64_t)(256 * s), idesc64, true);
 }
 
 // =============================================================================================
@@ -76,6 +81,7 @@ struct H4AnalysisParams {
   long T, F;
   int off;               // 256 (offline only: streaming blocks are far smaller than a tile)
   int parity;
+  int trim;              // edge K-steps without correction terms (h4_issue_mmas)
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
   long long* trace;      // [iterations][8 warps][8] clock64 stamps of CTA 0 (experiments/trace_h4.cu)
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     for (int r = 0; r < NQ; ++r) {
       const int q = tid + kH4Workers * r;
       const long s = s0 + 4L * q;
-      xr[r] = (q < G::ROWS * 16 && s >= 0 && s < p.T) ? __ldcs(reinterpret_cast<const float4*>(xrow + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xr[r] = (q < G::ROWS * 16 && s >= 0 && s < p.T) ? ptx::ldg128_na(reinterpret_cast<const float4*>(xrow + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   // D (TMEM) -> y: thread (row i, band half hb) owns frames 4 i .. 4 i + 3 of bands 8 hb .. 8 hb + 7: one float4 per band
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr);
+        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, 0, p.trim);
         ptx::umma_commit(&mma_bar[pb]);
       }
       __syncwarp();
@@ -271,6 +277,7 @@ struct H4SynthesisParams {
   long F;
   int o;                 // off2 / 16: 16 (PQMF.inverse) or 15 (CachedPQMF.inverse)
   int parity;
+  int trim;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
   long long* trace;
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, pad);
+        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, pad, p.trim);
         ptx::umma_commit(&mma_bar[pb]);
       }
       __syncwarp();
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       const float* sp = p.s + ((size_t)bb * 16 + 8 * ch) * p.F + n;
       const bool ok = has_item && n >= 0 && n + 3 < p.F;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? __ldcs(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     // D (TMEM) -> out.  Thread (row i, half hb) drains output frames 4 i + 2 hb, + 1 = 32 consecutive samples = four 32-byte
     // chunks, but rows are 256 B apart: stored like that, every warp store would touch 32 lines.  A 4 x 4 chunk transpose
@@ -550,6 +557,38 @@ inline void hankel4_build_banks(const float* hk /*[16][512]*/, int jlo, int kt, 
           img_synthesis[at] = part == 0 ? bits(c1) : bits(v - c1);
         }
       }
+}
+
+// Largest number of edge K-steps (per side, <= 7) whose correction terms may be dropped: the dropped terms are bounded by
+// 2 * 2^-11 * max|input| * (sum of the |bank| entries they multiply); returns the largest trim whose bound stays <= budget.
+inline int hankel4_pick_trim(const float* hk /*[16][512]*/, int jlo, int kt, bool synthesis, double budget) {
+  const int ks = kt / 16 + 3, dlo = jlo / 16, dhi = (jlo + kt) / 16 - 1;
+  int best = 0;
+  for (int trim = 1; trim <= 7 && ks - 2 * trim >= 1; ++trim) {
+    double worst = 0.0;
+    for (int delta = 0; delta < 4; ++delta)
+      for (int q = 0; q < 16; ++q) {   // q = band (analysis) or output phase (synthesis)
+        double sum = 0.0;
+        for (int side = 0; side < 2; ++side)
+          for (int t = 0; t < trim; ++t) {
+            const int s = side ? ks - 1 - t : t;
+            if (!synthesis) {
+              for (int e = 0; e < 16; ++e) {
+                const int j = 16 * s + e - 16 * delta;
+                if (j >= 0 && j < kt) sum += fabs((double)hk[q * 512 + jlo + j]);
+              }
+            } else {
+              const int d = dhi - s + delta;
+              if (d >= dlo && d <= dhi)
+                for (int k = 0; k < 16; ++k) sum += 16.0 * fabs((double)hk[k * 512 + 16 * d + q]);
+            }
+          }
+        worst = sum > worst ? sum : worst;
+      }
+    if (2.0 * worst / 2048.0 <= budget) best = trim;
+    else break;
+  }
+  return best;
 }
 
 }  // namespace pqmf

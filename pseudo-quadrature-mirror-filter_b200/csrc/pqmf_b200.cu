@@ -143,14 +143,14 @@ bool use_h4(int B, long F, const float* hist) { return hist == nullptr && (long)
 int h4_analysis(const float* x, float* y, const float* tables, int B, long T, long F, int off, unsigned flags, cudaStream_t st) {
   const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
   pqmf::H4AnalysisParams p{};
-  p.x = x; p.y = y; p.T = T; p.F = F; p.off = off; p.parity = 0;
+  p.x = x; p.y = y; p.T = T; p.F = F; p.off = off; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
   return trimmed ? pqmf::h4_launch_analysis<64, 384>(p, B, st) : pqmf::h4_launch_analysis<0, 512>(p, B, st);
 }
 int h4_synthesis(const float* s, float* out, const float* tables, int B, long F, int off2, unsigned flags, cudaStream_t st) {
   const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
   pqmf::H4SynthesisParams p{};
-  p.s = s; p.out = out; p.F = F; p.o = off2 / 16; p.parity = 0;
+  p.s = s; p.out = out; p.F = F; p.o = off2 / 16; p.parity = 0; p.trim = (int)((flags >> 20) & 7u);
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
   return trimmed ? pqmf::h4_launch_synthesis<64, 384>(p, B, st) : pqmf::h4_launch_synthesis<0, 512>(p, B, st);
 }
@@ -280,7 +280,11 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   // ---- part 3: the same bank replicated at four frame offsets for the offline default path (hankel4.cuh)
   uint16_t* img4 = reinterpret_cast<uint16_t*>(tables_host + kH4TableOffset);
   pqmf::hankel4_build_banks(hk_host, jlo, kt, img4, img4 + 2 * kH4ImageFloats);
-  if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32);
+  // edge K-steps of the Hankel-4 kernels that may skip the fp16 correction terms: worst-case added error, per unit of
+  // max|input|, 4e-6 (analysis) / 9e-6 (synthesis, all 16 bands at full scale); typical random-signal error is ~50x lower
+  const int trim_a = pqmf::hankel4_pick_trim(hk_host, jlo, kt, false, 4e-6);
+  const int trim_s = pqmf::hankel4_pick_trim(hk_host, jlo, kt, true, 9e-6);
+  if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s);
   return PQMF_OK;
 }
 

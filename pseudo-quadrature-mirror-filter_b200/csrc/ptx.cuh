@@ -162,6 +162,13 @@ __device__ __forceinline__ void ldg256_cs(const float* p, float (&v)[8]) {
                : "l"(p));
 }
 
+// streaming 128-bit load that does not allocate in L1 (the L1/shared data banks are the scarce resource of the Hankel kernels)
+__device__ __forceinline__ float4 ldg128_na(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // ---- packed fp32 (FFMA2) ----
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
