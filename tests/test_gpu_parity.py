@@ -255,3 +255,80 @@ def test_config2_properties_full_size(pq):
     assert a.abs().max().item() <= 2e-6
     # every batch row is processed independently and identically
     assert torch.equal(mod(x[5:6]), y[5:6])
+
+
+# ------------------------------------------------------------------ the offline n_band 16 default (Hankel-4 kernels) vs the oracle
+# These shapes have >= 96 tiles of 512 frames, so the dispatcher picks hankel4.cuh (smaller ones above run the fold kernels).
+@pytest.mark.parametrize("b,frames", ((24, 2048), (100, 516), (97, 515), (7, 512 * 14 + 8)))
+def test_hankel4_offline_vs_oracle(golden, pq, lib, b, frames):
+    hk = golden("bank_M16.npz")["hk"]
+    t = 16 * frames
+    x = O.audio_like((b, 1, t), 99 + frames)
+    mod = pq.PQMF(100, 16).cuda()
+    assert (mod._flags >> 17) & 7 and (mod._flags >> 20) & 7  # the default bank allows trimmed correction steps
+    y = mod(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0], hk)
+    assert np.abs(y - y64).max() <= TOL / 2
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
+    # the fold kernels (PQMF_FLAG_FOLD) and the Hankel-4 kernels are two implementations of the same arithmetic
+    tables = mod._tables
+    yf = torch.ops.pqmf_b200.analysis(dev(x), mod.hk, tables, frames, mod._flags | lib.PQMF_FLAG_FOLD)
+    assert (yf.cpu().numpy() - y).__abs__().max() <= 3e-6
+    of = torch.ops.pqmf_b200.synthesis(dev(s), mod.hk, tables, 0, mod._flags | lib.PQMF_FLAG_FOLD)
+    assert (of.cpu().numpy() - out).__abs__().max() <= 6e-6
+
+
+def test_hankel4_cached_offline_and_ragged(golden, pq):
+    """CachedPQMF offline on the Hankel-4 path: ceil(T/M) frames, synthesis one frame later (o = 15: no alignment pad)."""
+    hk = golden("bank_M16.npz")["hk"]
+    b, t = 26, 16 * 2048 - 5
+    x = O.audio_like((b, 1, t), 7)
+    mod = pq.CachedPQMF(100, 16).cuda()
+    y = mod(dev(x)).cpu().numpy()
+    assert y.shape[-1] == 2048
+    y64 = O.analysis(x[:, 0], hk, n_frames=2048)
+    assert np.abs(y - y64).max() <= TOL / 2
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.abs(out[:, 0] - O.synthesis(s, hk, delay_frames=1)).max() <= TOL / 2
+
+
+def test_hankel4_worst_case_signals(golden, pq):
+    """Inputs built to maximise what the trimmed correction steps drop: full-scale values whose signs follow the bank's
+    tails (analysis) and all sixteen sub-bands at full scale with aligned signs (synthesis)."""
+    hk = golden("bank_M16.npz")["hk"].astype(np.float64)
+    b, frames = 24, 2048
+    t = 16 * frames
+    rng = np.random.default_rng(5)
+    # analysis: x[n*16 + j - 256] = sign(hk[k, j]) for one band k per row, tiled along time with period 512 (a square-ish wave)
+    x = np.empty((b, 1, t), np.float32)
+    for r in range(b):
+        pat = np.sign(hk[r % 16])
+        pat[pat == 0] = 1.0
+        x[r, 0] = np.tile(pat, t // 512 + 1)[:t] * (1.0 - 2.0 ** -12)  # not exactly representable in fp16
+    mod = pq.PQMF(100, 16).cuda()
+    y = mod(dev(x)).cpu().numpy()
+    assert np.abs(y - O.analysis(x[:, 0].astype(np.float64), hk)).max() <= TOL
+    # synthesis: every band at +-(1 - 2^-12) with random signs held for 32 frames
+    s = (rng.integers(0, 2, (b, 16, frames // 32)) * 2 - 1).repeat(32, axis=2).astype(np.float32) * np.float32(1.0 - 2.0 ** -12)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    ref = O.synthesis(s.astype(np.float64), hk)
+    assert np.abs(out[:, 0] - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+
+
+def test_hankel4_full_length_bank(golden, pq):
+    """attenuation 120: the prototype no longer leaves 64 zero taps on each side, so the 512-tap instantiations run."""
+    g = golden("bank_M16_att120.npz")
+    hk = g["hk"]
+    mod = pq.PQMF(120, 16).cuda()
+    assert np.abs(mod.hk.cpu().numpy() - hk).max() <= 1e-7
+    b, frames = 24, 2048
+    x = O.audio_like((b, 1, 16 * frames), 120)
+    y = mod(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0], hk)
+    assert np.abs(y - y64).max() <= TOL / 2
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
