@@ -58,6 +58,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int, period_s: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period_s, [], set(), None
+        self.power_w = []
         self._halt = threading.Event()
         self.ok = False
         try:
@@ -85,6 +86,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
                     mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
@@ -100,7 +105,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=1.0)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "power_w_max": (round(max(self.power_w), 1) if self.power_w else None)}
 
 
 def physical_gpu_index(local_rank: int) -> int:
@@ -296,7 +301,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")

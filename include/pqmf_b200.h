@@ -38,7 +38,7 @@ extern "C" {
 #define PQMF_ERR_NO_DEVICE (-3)   /* no CUDA device / wrong architecture (needs sm_100)          */
 
 /* flags */
-#define PQMF_FLAG_EXACT 1u   /* force the direct-form kernels (bit-faithful to the registered hk)      */
+#define PQMF_FLAG_EXACT 1u   /* direct form with every term of the registered hk (no fold factorisation, no trimmed steps) */
 #define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
                               * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
 
@@ -53,18 +53,20 @@ typedef void* pqmf_stream_t; /* cudaStream_t */
 int pqmf_abi_version(void);
 const char* pqmf_strerror(int code);
 
-/* Which kernel family a call with these parameters would use: 0 = direct form (generic),
- * 1 = fold + tensor-core modulation fast path (n_band 16, L 512).  `tables` may be NULL. */
+/* Which kernel family a call with these parameters would use: 0 = register-tiled direct form (generic),
+ * 1 = the n_band 16 / L 512 tensor-core kernels (Hankel-4 offline, fold + modulation for streaming blocks and small
+ * batches, Hankel-16 with PQMF_FLAG_EXACT).  `tables` may be NULL. */
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
 
 /* ---- coefficient tables for the fast path (host side, one-off; replaces nothing in the reference:
  *      the reference re-derives its polyphase weights on every call, pqmf.py:128, :148-149) ----
  * Factorises hk[k, r + 2M q] ~= g[r + 2M q] * C[k, r] from the fp32 prototype h
  * (buffer `h`, pqmf.py:231) and returns the largest |hk - g (x) C| in *residual (may be NULL).
- * tables_host must hold pqmf_tables_numel(M, L) floats: [ g (L) | C_hi (M*2M) | C_lo (M*2M) ].
- * *fast_flags (may be NULL) receives the PQMF_FLAG_TAPS(...) bits describing which taps of g are pure zero
- * padding; OR them into the `flags` of the compute calls that are given these tables (optional: without them
- * the kernels run all L/2M taps).
+ * tables_host must hold pqmf_tables_numel(M, L) floats: [ g (L) | C_hi (M*2M) | C_lo (M*2M) ] followed by the fp16 images of
+ * hk in the tensor cores' shared-memory operand layout (Hankel-16 and Hankel-4 kernels, analysis and synthesis).
+ * *fast_flags (may be NULL) receives the PQMF_FLAG_TAPS(...) bits describing which taps are pure zero padding and the
+ * PQMF_FLAG_H4_TRIM(...) bits; OR them into the `flags` of the compute calls that are given these tables (optional:
+ * without them the kernels run all L/2M taps and every correction term).
  * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path. */
 long pqmf_tables_numel(int M, int L);
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -366,7 +367,12 @@ int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host,
   // Row chunks of ~16 MiB of input: H2D(i+1), the two kernels of chunk i and D2H(i-1) overlap (PCIe is full duplex),
   // each chunk on its own stream.  The staging buffers live in a per-device workspace that is created on first use
   // and only ever grows, so steady-state calls do no allocation.
-  long rows_per_chunk = (16L << 20) / (T * (long)sizeof(float));
+  static const long chunk_bytes = [] {
+    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 16 MiB of input per chunk
+    const long v = e ? atol(e) : 0;
+    return (v > 0 && v <= 1024 ? v : 16L) << 20;
+  }();
+  long rows_per_chunk = chunk_bytes / (T * (long)sizeof(float));
   if (rows_per_chunk < 1) rows_per_chunk = 1;
   if (rows_per_chunk > B) rows_per_chunk = B;
   const size_t chunk_elems = (size_t)rows_per_chunk * T;
