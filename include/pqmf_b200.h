@@ -42,6 +42,7 @@ extern "C" {
 #define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
                               * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
 
+#define PQMF_FLAG_NO_PAIR 8u /* n_band 16 offline kernels: one CTA per SM instead of CTA pairs (measurement / debugging)              */
 #define PQMF_FLAG_FOLD 4u    /* n_band 16 only: force the fold + modulation kernels (the streaming kernels) offline too */
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* from pqmf_build_tables_f32 */
 /* from pqmf_build_tables_f32: edge K-steps (analysis, synthesis) of the offline n_band 16 kernels whose fp16 correction

@@ -21,6 +21,7 @@ _BUILD_HINT = "build it with:  python -c 'import __graft_entry__ as g; g.build()
 PQMF_FLAG_EXACT = 1
 PQMF_FLAG_NO_SIGN = 2
 PQMF_FLAG_FOLD = 4
+PQMF_FLAG_NO_PAIR = 8
 
 
 def _load():

@@ -51,7 +51,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
 
 // x: 2 tiles of 8192 samples (+ tail); h: [64 bank rows][KT]: rows 0-31 stand in for c1 (delta-major), 32-63 for c2
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ D,
-                                                                             long long* cyc, int reps) {
+                                                                             long long* cyc, int reps, int n128 = KS, int n64 = KS) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar[2];
   __shared__ uint32_t slot;
@@ -93,12 +93,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_kernel(con
         if (elect_one_sync()) {
           const uint64_t da = desc_sw128(smem_u32(sm));
           const uint64_t db128 = umma_desc(smem_u32(sm + OFF_B128), 1024, 128), db64 = umma_desc(smem_u32(sm + OFF_B64), 512, 128);
-#pragma unroll
-          for (int s = 0; s < KS; ++s) umma2_f16(tm + 128 * (r & 1), da + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db128 + (uint64_t)(128 * s), idesc128, s != 0);
-          if (reps > 1 || true) {
-#pragma unroll
-            for (int s = 0; s < KS; ++s) umma2_f16(tm + 128 * (r & 1), da + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db64 + (uint64_t)(64 * s), idesc64, true);
-          }
+          for (int s = 0; s < n128; ++s) umma2_f16(tm + 128 * (r & 1), da + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db128 + (uint64_t)(128 * s), idesc128, s != 0);
+          for (int s = 0; s < n64; ++s) umma2_f16(tm + 128 * (r & 1), da + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)), db64 + (uint64_t)(64 * s), idesc64, true);
           umma2_commit_mc(&bar[r & 1], 3);
         }
         __syncwarp();
@@ -155,5 +151,12 @@ int main() {
   long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
   printf("pipelined pair groups (27 x N=128 + 27 x N=64; each SM of the pair does one tile per group): %lld cycles per group [%s]\n", c, cudaGetErrorString(e));
   printf("  (single-CTA Hankel-4: ~3240 cycles per tile)\n");
+  const int shapes[][2] = {{27, 27}, {19, 27}, {23, 27}, {27, 0}, {0, 27}};
+  for (auto& sh : shapes) {
+    pair_kernel<<<148, 128, SMEM>>>(dx, dh, dD, dc, 200, sh[0], sh[1]);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+    printf("pair: %2d x N=128 + %2d x N=64 per group: %lld cycles (single CTA, same loop form: 3385 / 2868 / 3126 / 2050 / 1688)\n", sh[0], sh[1], c);
+  }
   return 0;
 }

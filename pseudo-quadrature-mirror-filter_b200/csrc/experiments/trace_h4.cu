@@ -21,10 +21,11 @@ int main(int argc, char** argv) {
     cudaMemcpy(bank, ia.data(), ia.size() * 2, cudaMemcpyHostToDevice);
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const bool pair = argc > 4 && atoi(argv[4]) != 0;
   H4AnalysisParams p{};
   p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim = argc > 3 ? atoi(argv[3]) : 0;
   for (int rep = 0; rep < 3; ++rep) {
-    int rc = h4_launch_analysis<64, 384>(p, B, 0);
+    int rc = (pair ? h4_launch_analysis<64, 384, true>(p, B, 0) : h4_launch_analysis<64, 384, false>(p, B, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
   }
@@ -33,12 +34,12 @@ int main(int argc, char** argv) {
   q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim = argc > 3 ? atoi(argv[3]) : 0;
   if (synth) {
     cudaMemset(tr, 0, 64 * 64 * 8);
-    h4_launch_synthesis<64, 384>(q, B, 0);
+    (pair ? h4_launch_synthesis<64, 384, true>(q, B, 0) : h4_launch_synthesis<64, 384, false>(q, B, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (e) { printf("synthesis cuda=%s\n", cudaGetErrorString(e)); return 1; }
   }
   cudaEventRecord(e0);
-  for (int rep = 0; rep < 20; ++rep) { if (synth) h4_launch_synthesis<64, 384>(q, B, 0); else h4_launch_analysis<64, 384>(p, B, 0); }
+  for (int rep = 0; rep < 20; ++rep) { if (synth) (pair ? h4_launch_synthesis<64, 384, true>(q, B, 0) : h4_launch_synthesis<64, 384, false>(q, B, 0)); else (pair ? h4_launch_analysis<64, 384, true>(p, B, 0) : h4_launch_analysis<64, 384, false>(p, B, 0)); }
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   printf("%s %s data: %.1f us per launch (20 back to back)\n", synth ? "synthesis" : "analysis", argc > 1 ? "random" : "zero", ms * 50.f);

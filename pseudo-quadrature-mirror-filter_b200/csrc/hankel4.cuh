@@ -41,12 +41,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t byte_lin) { return byte_lin ^ (((byte_lin >> 7) & 7u) << 4); }
 
-template <int KT>
+// PAIR: the kernel runs as a cluster of two CTAs (tcgen05 cta_group::2).  One M = 256 MMA covers the two CTAs' tiles; each
+// CTA holds only its half of the bank rows: rank 0 [c1 (64 rows) | c1 rows 0-31 again], rank 1 [c2 (64 rows) | c1 rows 32-63],
+// i.e. rows 0-63 are this rank's half of the N = 128 operand and rows 64-95 its half of the N = 64 operand (at the same
+// offset in both CTAs, because one descriptor addresses both).  Per SM and K-step the tensor pipe then reads 6 + 5 KB of
+// operands instead of 8 + 6 KB (experiments/probe_h4_pair.cu: 2380 vs 2868 cycles per tile for the trimmed schedule).
+template <int KT, bool PAIR = false>
 struct H4Geometry {
   static constexpr int KS = KT / 16 + 3;                        // K-steps: taps + the three extra frame offsets
   static constexpr int ROWS = kH4Rows + ((KS - 1) >> 2) + 1;    // 128-byte rows of one plane (covers the synthesis pad <= 3 too)
   static constexpr int PLANE = ((ROWS * 128 + 1023) / 1024) * 1024;
-  static constexpr int BANK = KS * 2 * 128 * 16;                // [2 KS chunks][128 rows][16 B]
+  static constexpr int BANK_ROWS = PAIR ? 96 : 128;
+  static constexpr int BANK = KS * 2 * BANK_ROWS * 16;          // [2 KS chunks][BANK_ROWS][16 B]
   static constexpr int OFF_BANK = 0;
   static constexpr int OFF_P = OFF_BANK + BANK;                 // [2 buffers][h1, h2]
   static constexpr int OFF_BAR = OFF_P + 4 * PLANE;
@@ -57,18 +63,26 @@ struct H4Geometry {
 // K-steps carry only the tails of the prototype: there the two correction terms (h1 c2, h2 c1) are below the error budget
 // that pqmf_build_tables_f32 checked against the actual bank, so those steps run h1 c1 alone (N = 64) and no h2 pass.
 // `pad` shifts the A windows by whole frames (synthesis alignment).
-template <int KS>
+template <int KS, bool PAIR>
 __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int pad, int trim) {
+  constexpr uint32_t kBankRows = PAIR ? 96 : 128;
   const uint64_t da1 = umma_desc_sw128(plane1_addr), da2 = umma_desc_sw128(plane2_addr);
-  const uint64_t db = ptx::umma_desc(bank_addr, 2048, 128);
-  constexpr uint32_t idesc128 = ptx::umma_idesc_f16(128, 128), idesc64 = ptx::umma_idesc_f16(128, 64);
+  const uint64_t db = ptx::umma_desc(bank_addr, kBankRows * 16, 128);                 // N = 128 operand: bank rows from 0
+  const uint64_t db64 = PAIR ? ptx::umma_desc(bank_addr + 64 * 16, kBankRows * 16, 128) : db;  // N = 64 operand
+  constexpr uint32_t m = PAIR ? 256 : 128;
+  constexpr uint32_t idesc128 = ptx::umma_idesc_f16(m, 128), idesc64 = ptx::umma_idesc_f16(m, 64);
+  constexpr uint32_t kStep = 2 * kBankRows;                                          // descriptor units (16 B) per K-step of the bank
   auto a_step = [&](int s) { return (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)); };  // 128 B per 4 frames, 32 B per frame
-  for (int s = trim; s < KS - trim; ++s) ptx::umma_f16(d_tmem, da1 + a_step(s), db + (uint64_t)(256 * s), idesc128, s != trim);
+  auto mma = [&](uint64_t a, uint64_t bdesc, uint32_t idesc, bool acc) {
+    if constexpr (PAIR) ptx::umma_pair_f16(d_tmem, a, bdesc, idesc, acc);
+    else ptx::umma_f16(d_tmem, a, bdesc, idesc, acc);
+  };
+  for (int s = trim; s < KS - trim; ++s) mma(da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != trim);
   for (int s = 0; s < trim; ++s) {
-    ptx::umma_f16(d_tmem, da1 + a_step(s), db + (uint64_t)(256 * s), idesc64, true);
-    ptx::umma_f16(d_tmem, da1 + a_step(KS - 1 - s), db + (uint64_t)(256 * (KS - 1 - s)), idesc64, true);
+    mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+    mma(da1 + a_step(KS - 1 - s), db64 + (uint64_t)(kStep * (KS - 1 - s)), idesc64, true);
   }
-  for (int s = trim; s < KS - trim; ++s) ptx::umma_f16(d_tmem, da2 + a_step(s), db + (uint64_t)(256 * s), idesc64, true);
+  for (int s = trim; s < KS - trim; ++s) mma(da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
 }
 
 // =============================================================================================
@@ -94,9 +108,9 @@ struct H4AnalysisParams {
 #define H4_STAMP(k) do { } while (0)
 #endif
 
-template <int JLO, int KT>
+template <int JLO, int KT, bool PAIR>
 __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisParams p) {
-  using G = H4Geometry<KT>;
+  using G = H4Geometry<KT, PAIR>;
   constexpr int KS = G::KS;
   constexpr int NQ = (G::ROWS * 16 + kH4Workers - 1) / kH4Workers;  // float4 loads per thread per tile (row = 16 quads)
   extern __shared__ __align__(1024) unsigned char h4_smem[];
@@ -110,31 +124,41 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
 
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int kMmaWarp = kH4Workers / 32;
+  // pfull lives in the leader CTA (rank 0): one arrival per worker warp of every CTA of the pair
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
   if (tid == 0) {
-    ptx::mbar_init(&pfull[0], kH4Workers);
-    ptx::mbar_init(&pfull[1], kH4Workers);
+    ptx::mbar_init(&pfull[0], (kH4Workers / 32) * (PAIR ? 2 : 1));
+    ptx::mbar_init(&pfull[1], (kH4Workers / 32) * (PAIR ? 2 : 1));
     ptx::mbar_init(&mma_bar[0], 1);
     ptx::mbar_init(&mma_bar[1], 1);
     ptx::mbar_init(bankfull, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_slot, 256);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, 256);
+    } else {
+      ptx::tmem_alloc(tmem_slot, 256);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
   ptx::tc_fence_after();
+  const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(pfull), 0) : 0u;
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) {
     ptx::mbar_arrive_expect_tx(bankfull, G::BANK);
-    ptx::bulk_g2s(bank, p.bank, G::BANK, bankfull);
+    ptx::bulk_g2s(bank, reinterpret_cast<const unsigned char*>(p.bank) + (size_t)rank * G::BANK, G::BANK, bankfull);  // PAIR: per-rank images
   }
 
   const unsigned tpr = (unsigned)p.tiles_per_row;
   const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
-  const unsigned n_iter = (unsigned)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;   // both CTAs of a pair run the same number of tiles:
+  const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
+  const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);      // a tile with b >= n_rows is padding (zeros in, nothing out)
 #ifdef PQMF_H4_TRACE
   long long cta_c0 = clock64(), cta_t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
@@ -149,7 +173,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     for (int r = 0; r < NQ; ++r) {
       const int q = tid + kH4Workers * r;
       const long s = s0 + 4L * q;
-      xr[r] = (q < G::ROWS * 16 && s >= 0 && s < p.T) ? ptx::ldg128_na(reinterpret_cast<const float4*>(xrow + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xr[r] = (bb < n_rows && q < G::ROWS * 16 && s >= 0 && s < p.T) ? ptx::ldg128_na(reinterpret_cast<const float4*>(xrow + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   // D (TMEM) -> y: thread (row i, band half hb) owns frames 4 i .. 4 i + 3 of bands 8 hb .. 8 hb + 7: one float4 per band
@@ -190,14 +214,14 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
   if (warp == kMmaWarp) {
     // ---- issuer warp: tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps the issuing
     //      thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
-    ptx::mbar_wait(bankfull, 0);
-    for (unsigned it = 0; it < n_iter; ++it) {
+    for (unsigned it = 0; rank == 0 && it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, 0, p.trim);
-        ptx::umma_commit(&mma_bar[pb]);
+        h4_issue_mmas<KS, PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, 0, p.trim);
+        if constexpr (PAIR) ptx::umma_pair_commit(&mma_bar[pb]);
+        else ptx::umma_commit(&mma_bar[pb]);
       }
       __syncwarp();
     }
@@ -228,7 +252,12 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     H4_STAMP(1);
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
-    ptx::mbar_arrive(&pfull[pb]);
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      if (it == 0) ptx::mbar_wait(bankfull, 0);   // this CTA's bank image has landed before its first arrival
+      if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
+      else ptx::mbar_arrive(&pfull[pb]);
+    }
     // prefetch the next tile's window (consumed at the top of the next iteration)
     unsigned nb = b + step_b, nc = c + step_c;
     if (nc >= tpr) {
@@ -242,7 +271,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
       ptx::tc_fence_after();
       H4_STAMP(4);
-      epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+      if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
     }
     H4_STAMP(5);
     prev_b = b;
@@ -252,7 +281,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
   }
   ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
   ptx::tc_fence_after();
-  epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+  if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
   ptx::tc_fence_before();
   __syncthreads();
@@ -264,7 +293,12 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     p.trace[64 * 64 + 2 * blockIdx.x + 1] = t1 - cta_t0;
   }
 #endif
-  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  if constexpr (PAIR) {
+    ptx::cluster_sync_all();   // the peer may still be read by / signalled from the leader's last MMAs
+    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
+  } else {
+    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  }
 }
 
 // =============================================================================================
@@ -287,9 +321,9 @@ struct H4SynthesisParams {
 constexpr int kH4SynWorkers = 288;                    // nine worker warps: 2 x ROWS (<= 274) load/convert items, one per thread
 constexpr int kH4SynThreads = kH4SynWorkers + 32;     // + the issuer warp
 
-template <int JLO, int KT>
+template <int JLO, int KT, bool PAIR>
 __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
-  using G = H4Geometry<KT>;
+  using G = H4Geometry<KT, PAIR>;
   constexpr int KS = G::KS;
   constexpr int EHI = (JLO + KT) / 16 - 1;        // largest frame lag with a non-zero tap
   static_assert(2 * G::ROWS <= kH4SynWorkers, "one (frame quad, band half) item per worker thread");
@@ -304,31 +338,41 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
 
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int kMmaWarp = kH4SynWorkers / 32;
+  // pfull lives in the leader CTA (rank 0): one arrival per worker warp of every CTA of the pair
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
   if (tid == 0) {
-    ptx::mbar_init(&pfull[0], kH4SynWorkers);
-    ptx::mbar_init(&pfull[1], kH4SynWorkers);
+    ptx::mbar_init(&pfull[0], (kH4SynWorkers / 32) * (PAIR ? 2 : 1));
+    ptx::mbar_init(&pfull[1], (kH4SynWorkers / 32) * (PAIR ? 2 : 1));
     ptx::mbar_init(&mma_bar[0], 1);
     ptx::mbar_init(&mma_bar[1], 1);
     ptx::mbar_init(bankfull, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_slot, 256);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, 256);
+    } else {
+      ptx::tmem_alloc(tmem_slot, 256);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
   ptx::tc_fence_after();
+  const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(pfull), 0) : 0u;
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) {
     ptx::mbar_arrive_expect_tx(bankfull, G::BANK);
-    ptx::bulk_g2s(bank, p.bank, G::BANK, bankfull);
+    ptx::bulk_g2s(bank, reinterpret_cast<const unsigned char*>(p.bank) + (size_t)rank * G::BANK, G::BANK, bankfull);  // PAIR: per-rank images
   }
 
   const unsigned tpr = (unsigned)p.tiles_per_row;
   const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
-  const unsigned n_iter = (unsigned)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;   // both CTAs of a pair run the same number of tiles:
+  const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
+  const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);      // a tile with b >= n_rows is padding (zeros in, nothing out)
 
   // plane frame m <-> sub-band frame n = 512 c + (o - EHI - pad) + m, pad = (o - EHI) mod 4, so that frame quads are
   // 16-byte aligned in global memory; K-step s of row i then reads plane frame 4 i + s + pad.
@@ -337,14 +381,14 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
   const uint32_t bank_addr = ptx::smem_u32(bank), plane_addr = ptx::smem_u32(planes);
   if (warp == kMmaWarp) {
     // ---- issuer warp (see the analysis kernel)
-    ptx::mbar_wait(bankfull, 0);
-    for (unsigned it = 0; it < n_iter; ++it) {
+    for (unsigned it = 0; rank == 0 && it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, pad, p.trim);
-        ptx::umma_commit(&mma_bar[pb]);
+        h4_issue_mmas<KS, PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, pad, p.trim);
+        if constexpr (PAIR) ptx::umma_pair_commit(&mma_bar[pb]);
+        else ptx::umma_commit(&mma_bar[pb]);
       }
       __syncwarp();
     }
@@ -358,7 +402,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     auto load_frames = [&](unsigned bb, unsigned cc) {
       const long n = (long)cc * kH4Frames + nbase + 4 * m4;
       const float* sp = p.s + ((size_t)bb * 16 + 8 * ch) * p.F + n;
-      const bool ok = has_item && n >= 0 && n + 3 < p.F;
+      const bool ok = bb < n_rows && has_item && n >= 0 && n + 3 < p.F;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -438,7 +482,12 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       H4_STAMP(1);
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&pfull[pb]);
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        if (it == 0) ptx::mbar_wait(bankfull, 0);
+        if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
+        else ptx::mbar_arrive(&pfull[pb]);
+      }
       unsigned nb = b + step_b, nc = c + step_c;
       if (nc >= tpr) {
         nc -= tpr;
@@ -452,7 +501,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
         ptx::tc_fence_after();
         H4_STAMP(4);
-        if (warp < 8) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+        if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
       }
       H4_STAMP(5);
       prev_b = b;
@@ -462,11 +511,16 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     }
     ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
     ptx::tc_fence_after();
-    if (warp < 8) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+    if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  if constexpr (PAIR) {
+    ptx::cluster_sync_all();   // the peer may still be read by / signalled from the leader's last MMAs
+    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
+  } else {
+    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -492,36 +546,47 @@ inline int h4_configure(Kern kern, int bytes, bool (&configured)[64], int& sm_co
   return 0;
 }
 
-template <int JLO, int KT>
-int h4_launch_analysis(H4AnalysisParams p, int B, cudaStream_t st) {
-  using G = H4Geometry<KT>;
-  auto kern = h4_analysis_kernel<JLO, KT>;
-  static bool configured[64] = {false};
+// one CTA (or CTA pair) per SM, static round-robin over the tiles; PAIR launches clusters of two
+template <bool PAIR, typename Kern, typename Params>
+inline int h4_launch(Kern kern, Params p, int B, int threads, int bytes, bool (&configured)[64], cudaStream_t st) {
   int sms = 0;
-  if (int e = h4_configure(kern, G::BYTES, configured, sms)) return e;
+  if (int e = h4_configure(kern, bytes, configured, sms)) return e;
   p.tiles_per_row = (p.F + kH4Frames - 1) / kH4Frames;
   p.n_tiles = p.tiles_per_row * B;
   if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
-  long grid = sms;
-  if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, kH4Threads, G::BYTES, st>>>(p);
-  return (int)cudaGetLastError();
+  long grid = PAIR ? (sms & ~1) : sms;
+  const long want = PAIR ? ((p.n_tiles + 1) & ~1L) : p.n_tiles;
+  if (grid > want) grid = want;
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, p);
+  } else {
+    kern<<<(unsigned)grid, threads, bytes, st>>>(p);
+    return (int)cudaGetLastError();
+  }
 }
 
-template <int JLO, int KT>
-int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
-  using G = H4Geometry<KT>;
-  auto kern = h4_synthesis_kernel<JLO, KT>;
+template <int JLO, int KT, bool PAIR = false>
+int h4_launch_analysis(H4AnalysisParams p, int B, cudaStream_t st) {
   static bool configured[64] = {false};
-  int sms = 0;
-  if (int e = h4_configure(kern, G::BYTES, configured, sms)) return e;
-  p.tiles_per_row = (p.F + kH4Frames - 1) / kH4Frames;
-  p.n_tiles = p.tiles_per_row * B;
-  if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
-  long grid = sms;
-  if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<(unsigned)grid, kH4SynThreads, G::BYTES, st>>>(p);
-  return (int)cudaGetLastError();
+  return h4_launch<PAIR>(h4_analysis_kernel<JLO, KT, PAIR>, p, B, kH4Threads, H4Geometry<KT, PAIR>::BYTES, configured, st);
+}
+
+template <int JLO, int KT, bool PAIR = false>
+int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
+  static bool configured[64] = {false};
+  return h4_launch<PAIR>(h4_synthesis_kernel<JLO, KT, PAIR>, p, B, kH4SynThreads, H4Geometry<KT, PAIR>::BYTES, configured, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -556,6 +621,18 @@ inline void hankel4_build_banks(const float* hk /*[16][512]*/, int jlo, int kt, 
           const float c1 = __half2float(__float2half_rn(v));
           img_synthesis[at] = part == 0 ? bits(c1) : bits(v - c1);
         }
+      }
+}
+
+// per-rank images for the CTA-pair kernels: [rank][2 KS][96 rows][8]; rows 0-63 = rows 64 rank .. of the single-CTA image (rank 0:
+// c1, rank 1: c2), rows 64-95 = c1 rows 32 rank .. 32 rank + 31 (this rank's half of the N = 64 operand)
+inline void hankel4_pair_image(const uint16_t* single /*[2 KS][128][8]*/, int kt, uint16_t* pair /*[2][2 KS][96][8]*/) {
+  const int chunks = 2 * (kt / 16 + 3);
+  for (int r = 0; r < 2; ++r)
+    for (int kc = 0; kc < chunks; ++kc)
+      for (int row = 0; row < 96; ++row) {
+        const int src = row < 64 ? 64 * r + row : 32 * r + (row - 64);
+        memcpy(pair + (((size_t)r * chunks + kc) * 96 + row) * 8, single + ((size_t)kc * 128 + src) * 8, 16);
       }
 }
 

@@ -138,6 +138,8 @@ constexpr long kFoldTableFloats = 512 + 2 * 16 * 32;  // [ g | c1 | c2 ] of the 
 constexpr long kH16ImageFloats = 512L * 16;            // one hankel16 bank image (fp16 [KT/8][32][8]), sized for KT = 512
 constexpr long kH4TableOffset = kFoldTableFloats + 2 * kH16ImageFloats;
 constexpr long kH4ImageFloats = 35L * 4096 / 4;        // one hankel4 bank image (fp16 [2 KS][128][8]), sized for KS = 35
+constexpr long kH4PairOffset = kH4TableOffset + 2 * kH4ImageFloats;
+constexpr long kH4PairImageFloats = 2L * 35 * 3072 / 4;  // per-rank images of the CTA-pair kernels (fp16 [2][2 KS][96][8])
 
 // offline n_band 16 default: four-frames-per-row Hankel GEMM (hankel4.cuh) when there are enough 512-frame tiles
 bool use_h4(int B, long F, const float* hist) { return hist == nullptr && (long)B * ((F + 511) / 512) >= 96; }
@@ -145,6 +147,10 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
   pqmf::H4AnalysisParams p{};
   p.x = x; p.y = y; p.T = T; p.F = F; p.off = off; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
+  if (!(flags & PQMF_FLAG_NO_PAIR)) {
+    p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset);
+    return trimmed ? pqmf::h4_launch_analysis<64, 384, true>(p, B, st) : pqmf::h4_launch_analysis<0, 512, true>(p, B, st);
+  }
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
   return trimmed ? pqmf::h4_launch_analysis<64, 384>(p, B, st) : pqmf::h4_launch_analysis<0, 512>(p, B, st);
 }
@@ -152,6 +158,10 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
   const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
   pqmf::H4SynthesisParams p{};
   p.s = s; p.out = out; p.F = F; p.o = off2 / 16; p.parity = 0; p.trim = (int)((flags >> 20) & 7u);
+  if (!(flags & PQMF_FLAG_NO_PAIR)) {
+    p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset + kH4PairImageFloats);
+    return trimmed ? pqmf::h4_launch_synthesis<64, 384, true>(p, B, st) : pqmf::h4_launch_synthesis<0, 512, true>(p, B, st);
+  }
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
   return trimmed ? pqmf::h4_launch_synthesis<64, 384>(p, B, st) : pqmf::h4_launch_synthesis<0, 512>(p, B, st);
 }
@@ -225,7 +235,7 @@ unsigned long long pqmf_launch_count(void) { return g_launches.load(); }
 
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags) { return use_fast(M, L, tables, flags) ? 1 : 0; }
 
-long pqmf_tables_numel(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4TableOffset + 2L * kH4ImageFloats : 0; }
+long pqmf_tables_numel(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4PairOffset + 2L * kH4PairImageFloats : 0; }
 
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
                           double* residual, unsigned* fast_flags) {
@@ -281,6 +291,9 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   // ---- part 3: the same bank replicated at four frame offsets for the offline default path (hankel4.cuh)
   uint16_t* img4 = reinterpret_cast<uint16_t*>(tables_host + kH4TableOffset);
   pqmf::hankel4_build_banks(hk_host, jlo, kt, img4, img4 + 2 * kH4ImageFloats);
+  uint16_t* imgp = reinterpret_cast<uint16_t*>(tables_host + kH4PairOffset);
+  pqmf::hankel4_pair_image(img4, kt, imgp);
+  pqmf::hankel4_pair_image(img4 + 2 * kH4ImageFloats, kt, imgp + 2 * kH4PairImageFloats);
   // edge K-steps of the Hankel-4 kernels that may skip the fp16 correction terms: worst-case added error, per unit of
   // max|input|, 4e-6 (analysis) / 9e-6 (synthesis, all 16 bands at full scale); typical random-signal error is ~50x lower
   const int trim_a = pqmf::hankel4_pick_trim(hk_host, jlo, kt, false, 4e-6);
