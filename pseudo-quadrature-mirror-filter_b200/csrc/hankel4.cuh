@@ -1,17 +1,19 @@
 // n_band = 16 PQMF, offline fast path: the direct form as an implicit-Hankel GEMM with FOUR frames per operand row.
 //
 // hankel16.cuh shows that a strided signal can be fed to tcgen05.mma without im2col (one frame = 32 B = the SWIZZLE_32B row
-// pitch), but there every 16 taps cost a full shared-memory read of the 128-row A tile (96 B/sample: smem-bound at ~40 % of
+// pitch), but there every 16 taps cost a full shared-memory read of the 128-row A tile (~111 B/sample: smem-bound at ~30 % of
 // the HBM roofline).  Here one A row holds FOUR frames (64 samples = 128 B in fp16 = the SWIZZLE_128B row pitch) and the
 // bank is replicated at the four frame offsets along N:
 //   analysis : D[i, (delta, k)] = sum_kappa X[64 i + kappa] * hk[k, kappa - 16 delta]      = y[k, frame 4 i + delta]
 //   synthesis: D[i, (delta, p)] = sum_(e,k) S^T[4 i + o - e, k] * 16 hk[k, 16 (e + delta) + p] = out[16 (4 i + delta) + p]
-// so one 128-row MMA (N = 128) yields 512 frames, each signal byte is read from shared memory 4x less often
-// (~46 B/sample), and the tensor pipe (27 x [N=128 + N=64] MMAs = 2592 cycles per 8192 samples) sits just under the HBM
-// time of the same tile (2664 cycles at 6.55 TB/s, 1.8 GHz).  K-step s reads rows starting at byte 128 (s / 4) + 32 (s % 4).
+// so one 128-row MMA (N = 128) yields 512 frames and each signal byte is read from shared memory 4x less often.
+// K-step s reads rows starting at byte 128 (s / 4) + 32 (s % 4).
 // Precision: the same two-term fp16 split as hankel16.cuh (exact in hk up to 2^-22), columns 0-63 main term, 64-127 the
-// c2 correction; the second pass (h2) uses only the c1 half (N = 64).
-// CUDA cores only convert fp32 -> 2 x fp16 (swizzled STS) and drain TMEM: ~8 thread-instructions per sample.
+// c2 correction; the second pass (h2) uses only the c1 half (N = 64).  Edge K-steps whose correction terms are provably
+// negligible for the actual bank run the main term only (h4_issue_mmas, hankel4_pick_trim).
+// Roles: worker warps convert fp32 -> 2 x fp16 planes (swizzled STS) and drain TMEM; ONE warp only issues the MMAs
+// (tcgen05.mma issue blocks the issuing thread while the tensor queue is full).  With PAIR the kernel runs as clusters of two
+// CTAs sharing the bank operand (cta_group::2).  DESIGN.md section 5 has the measurements behind each of these choices.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -226,62 +228,62 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       __syncwarp();
     }
   } else {
-  load_window(b, c);
-  unsigned prev_b = 0, prev_c = 0;
-  for (unsigned it = 0; it < n_iter; ++it) {
-    const int pb = (int)(it & 1);
-    H4_STAMP(0);
-    // ---- fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples).  planes[pb] were last read by the MMAs of
-    //      tile it-2, whose completion this thread observed before draining tile it-2.
-    {
-      unsigned char* p1 = planes + (2 * pb) * G::PLANE;
-      unsigned char* p2 = p1 + G::PLANE;
+    load_window(b, c);
+    unsigned prev_b = 0, prev_c = 0;
+    for (unsigned it = 0; it < n_iter; ++it) {
+      const int pb = (int)(it & 1);
+      H4_STAMP(0);
+      // ---- fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples).  planes[pb] were last read by the MMAs of
+      //      tile it-2, whose completion this thread observed before draining tile it-2.
+      {
+        unsigned char* p1 = planes + (2 * pb) * G::PLANE;
+        unsigned char* p2 = p1 + G::PLANE;
 #pragma unroll
-      for (int r = 0; r < NQ; ++r) {
-        const int q = tid + kH4Workers * r;
-        if (q < G::ROWS * 16) {
-          uint2 a, bq;
-          split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
-          split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
-          const uint32_t o = sw128_offset((uint32_t)q * 8u);
-          *reinterpret_cast<uint2*>(p1 + o) = a;
-          *reinterpret_cast<uint2*>(p2 + o) = bq;
+        for (int r = 0; r < NQ; ++r) {
+          const int q = tid + kH4Workers * r;
+          if (q < G::ROWS * 16) {
+            uint2 a, bq;
+            split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
+            split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
+            const uint32_t o = sw128_offset((uint32_t)q * 8u);
+            *reinterpret_cast<uint2*>(p1 + o) = a;
+            *reinterpret_cast<uint2*>(p2 + o) = bq;
+          }
         }
       }
+      H4_STAMP(1);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        if (it == 0) ptx::mbar_wait(bankfull, 0);   // this CTA's bank image has landed before its first arrival
+        if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
+        else ptx::mbar_arrive(&pfull[pb]);
+      }
+      // prefetch the next tile's window (consumed at the top of the next iteration)
+      unsigned nb = b + step_b, nc = c + step_c;
+      if (nc >= tpr) {
+        nc -= tpr;
+        ++nb;
+      }
+      if (it + 1 < n_iter) load_window(nb, nc);
+      H4_STAMP(2);
+      H4_STAMP(3);
+      if (it > 0) {
+        ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        H4_STAMP(4);
+        if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+      }
+      H4_STAMP(5);
+      prev_b = b;
+      prev_c = c;
+      b = nb;
+      c = nc;
     }
-    H4_STAMP(1);
-    ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncwarp();
-    if ((tid & 31) == 0) {
-      if (it == 0) ptx::mbar_wait(bankfull, 0);   // this CTA's bank image has landed before its first arrival
-      if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
-      else ptx::mbar_arrive(&pfull[pb]);
-    }
-    // prefetch the next tile's window (consumed at the top of the next iteration)
-    unsigned nb = b + step_b, nc = c + step_c;
-    if (nc >= tpr) {
-      nc -= tpr;
-      ++nb;
-    }
-    if (it + 1 < n_iter) load_window(nb, nc);
-    H4_STAMP(2);
-    H4_STAMP(3);
-    if (it > 0) {
-      ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-      ptx::tc_fence_after();
-      H4_STAMP(4);
-      if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
-    }
-    H4_STAMP(5);
-    prev_b = b;
-    prev_c = c;
-    b = nb;
-    c = nc;
-  }
-  ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-  ptx::tc_fence_after();
-  if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+    ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
   ptx::tc_fence_before();
   __syncthreads();
