@@ -10,6 +10,7 @@
 #include <ATen/ATen.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <torch/csrc/autograd/custom_function.h>
 #include <torch/library.h>
 
 #include "../../include/pqmf_b200.h"
@@ -135,6 +136,77 @@ at::Tensor synthesis_stream(const at::Tensor& s, const at::Tensor& hk, const at:
 
 int64_t launch_count() { return (int64_t)pqmf_launch_count(); }
 
+// ---- autograd (the reference path is differentiable, upstream users train through PQMF) --------------------
+// Analysis and synthesis are each other's transposes up to the gain M and the frame delay, so both backward passes are the
+// opposite-direction kernel with the same bank:
+//   d/dx  analysis  : grad_x[t]   = sum_{k,n} sigma(k,n) gy[k,n] hk[k, t - nM + L/2]                 = synthesis(gy, delay 0)[t] / M
+//   d/ds  synthesis : grad_s[k,n] = M sigma(k,n) sum_tau g[tau] hk[k, tau - (n + d) M + L/2] = M sigma(k,n) sigma(k,n+d) analysis(g)[k, n + d]
+// (sigma(k,n) sigma(k,n+1) = (-1)^k; with PQMF_FLAG_NO_SIGN neither direction applies sigma and the factor is 1).
+at::Tensor call_analysis(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, int64_t flags) {
+  static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("pqmf_b200::analysis", "").typed<decltype(analysis)>();
+  return op.call(x, hk, tables, n_frames, flags);
+}
+at::Tensor call_synthesis(const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables, int64_t delay_frames, int64_t flags) {
+  static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("pqmf_b200::synthesis", "").typed<decltype(synthesis)>();
+  return op.call(s, hk, tables, delay_frames, flags);
+}
+
+struct AnalysisFn : public torch::autograd::Function<AnalysisFn> {
+  static at::Tensor forward(torch::autograd::AutogradContext* ctx, const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables,
+                            int64_t n_frames, int64_t flags) {
+    at::AutoDispatchBelowADInplaceOrView guard;
+    ctx->save_for_backward({hk, tables});
+    ctx->saved_data["T"] = x.size(-1);
+    ctx->saved_data["flags"] = flags;
+    return call_analysis(x, hk, tables, n_frames, flags);
+  }
+  static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx, torch::autograd::variable_list grads) {
+    const auto saved = ctx->get_saved_variables();
+    const at::Tensor &hk = saved[0], &tables = saved[1];
+    const int64_t T = ctx->saved_data["T"].toInt(), flags = ctx->saved_data["flags"].toInt(), M = hk.size(0);
+    at::Tensor gy = grads[0].contiguous();
+    const int64_t F = gy.size(-1), need = (T + M - 1) / M;   // frames whose synthesis output covers [0, T)
+    if (need > F) gy = at::constant_pad_nd(gy, {0, need - F});
+    at::Tensor gx = call_synthesis(gy, hk, tables, 0, flags);
+    gx = gx.slice(-1, 0, T) * (1.0 / (double)M);
+    return {gx, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
+  }
+};
+
+struct SynthesisFn : public torch::autograd::Function<SynthesisFn> {
+  static at::Tensor forward(torch::autograd::AutogradContext* ctx, const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables,
+                            int64_t delay_frames, int64_t flags) {
+    at::AutoDispatchBelowADInplaceOrView guard;
+    ctx->save_for_backward({hk, tables});
+    ctx->saved_data["delay"] = delay_frames;
+    ctx->saved_data["flags"] = flags;
+    return call_synthesis(s, hk, tables, delay_frames, flags);
+  }
+  static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx, torch::autograd::variable_list grads) {
+    const auto saved = ctx->get_saved_variables();
+    const at::Tensor &hk = saved[0], &tables = saved[1];
+    const int64_t d = ctx->saved_data["delay"].toInt(), flags = ctx->saved_data["flags"].toInt(), M = hk.size(0);
+    const at::Tensor g = grads[0].contiguous();          // [B, C, M F]
+    const int64_t F = g.size(-1) / M;
+    at::Tensor a = call_analysis(g, hk, tables, F + d, flags);   // [B, C M, F + d]
+    if (d > 0) {
+      a = a.slice(-1, d, F + d);
+      if (!(flags & PQMF_FLAG_NO_SIGN) && (d & 1)) {
+        const at::Tensor sign = 1.0 - 2.0 * at::arange(a.size(1), a.options()).remainder((double)M).remainder(2.0);
+        a = a * sign.view({1, -1, 1});
+      }
+    }
+    return {a * (double)M, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
+  }
+};
+
+at::Tensor analysis_autograd(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, int64_t flags) {
+  return AnalysisFn::apply(x, hk, tables, n_frames, flags);
+}
+at::Tensor synthesis_autograd(const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables, int64_t delay_frames, int64_t flags) {
+  return SynthesisFn::apply(s, hk, tables, delay_frames, flags);
+}
+
 }  // namespace
 
 TORCH_LIBRARY(pqmf_b200, m) {
@@ -154,4 +226,10 @@ TORCH_LIBRARY_IMPL(pqmf_b200, CUDA, m) {
   m.impl("synthesis", &synthesis);
   m.impl("analysis_stream", &analysis_stream);
   m.impl("synthesis_stream", &synthesis_stream);
+}
+
+// gradients w.r.t. the signal / the sub-bands only (the bank is a registered buffer in the reference, not a parameter)
+TORCH_LIBRARY_IMPL(pqmf_b200, Autograd, m) {
+  m.impl("analysis", &analysis_autograd);
+  m.impl("synthesis", &synthesis_autograd);
 }
