@@ -149,7 +149,9 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   p.x = x; p.y = y; p.T = T; p.F = F; p.off = off; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset);
-    return trimmed ? pqmf::h4_launch_analysis<64, 384, true>(p, B, st) : pqmf::h4_launch_analysis<0, 512, true>(p, B, st);
+    const int e = trimmed ? pqmf::h4_launch_analysis<64, 384, true>(p, B, st) : pqmf::h4_launch_analysis<0, 512, true>(p, B, st);
+    if (e == 0) return 0;
+    (void)cudaGetLastError();   // a context that cannot co-schedule CTA pairs (e.g. an SM partition): same arithmetic, one CTA per SM
   }
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
   return trimmed ? pqmf::h4_launch_analysis<64, 384>(p, B, st) : pqmf::h4_launch_analysis<0, 512>(p, B, st);
@@ -160,7 +162,9 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
   p.s = s; p.out = out; p.F = F; p.o = off2 / 16; p.parity = 0; p.trim = (int)((flags >> 20) & 7u);
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset + kH4PairImageFloats);
-    return trimmed ? pqmf::h4_launch_synthesis<64, 384, true>(p, B, st) : pqmf::h4_launch_synthesis<0, 512, true>(p, B, st);
+    const int e = trimmed ? pqmf::h4_launch_synthesis<64, 384, true>(p, B, st) : pqmf::h4_launch_synthesis<0, 512, true>(p, B, st);
+    if (e == 0) return 0;
+    (void)cudaGetLastError();
   }
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
   return trimmed ? pqmf::h4_launch_synthesis<64, 384>(p, B, st) : pqmf::h4_launch_synthesis<0, 512>(p, B, st);
@@ -424,16 +428,25 @@ int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host,
   check(cudaMemcpyAsync(d_hk, hk_host, bank_elems * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
   if (n_tab) check(cudaMemcpyAsync(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
   check(cudaStreamSynchronize(ws.st[0]));
+  // Chunk schedule: small chunks at both ends (1, 1, 2 rows-per-chunk/4 ... ) shorten the pipeline fill (nothing overlaps the
+  // first H2D) and drain (nothing overlaps the last D2H); full chunks in between keep the kernels efficient.
   int slot = 0;
-  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += rows_per_chunk, slot = (slot + 1) % kHostSlots) {
-    const int rows = (int)((B - r0 < rows_per_chunk) ? (B - r0) : rows_per_chunk);
+  long rows = 0;
+  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += rows, slot = (slot + 1) % kHostSlots) {
+    const long left = B - r0, done = r0;
+    long want = rows_per_chunk;
+    const long ramp_in = done < rows_per_chunk ? (done < 2 ? rows_per_chunk / 4 : rows_per_chunk / 2) : rows_per_chunk;
+    const long ramp_out = left <= rows_per_chunk ? (left <= rows_per_chunk / 2 ? rows_per_chunk / 4 : rows_per_chunk / 2) : rows_per_chunk;
+    want = ramp_in < ramp_out ? ramp_in : ramp_out;
+    if (want < 1) want = 1;
+    rows = left < want ? left : want;
     const size_t n = (size_t)rows * T;
     cudaStream_t s = ws.st[slot];
     check(cudaMemcpyAsync(ws.d_x[slot], x_host + (size_t)r0 * T, n * sizeof(float), cudaMemcpyHostToDevice, s));
     if (rc) break;
-    rc = pqmf_analysis_f32(ws.d_x[slot], ws.d_y[slot], d_hk, d_tab, rows, T, F, M, L, flags, s);
+    rc = pqmf_analysis_f32(ws.d_x[slot], ws.d_y[slot], d_hk, d_tab, (int)rows, T, F, M, L, flags, s);
     if (rc) break;
-    rc = pqmf_synthesis_f32(ws.d_y[slot], ws.d_o[slot], d_hk, d_tab, rows, F, M, L, delay_frames, flags, s);
+    rc = pqmf_synthesis_f32(ws.d_y[slot], ws.d_o[slot], d_hk, d_tab, (int)rows, F, M, L, delay_frames, flags, s);
     if (rc) break;
     if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * T, ws.d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
     check(cudaMemcpyAsync(out_host + (size_t)r0 * T, ws.d_o[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
