@@ -6,6 +6,7 @@
 #include "../hankel4.cuh"
 using namespace pqmf;
 int main(int argc, char** argv) {
+  const bool pair = argc > 4 && atoi(argv[4]) != 0;
   const int B = 64; const long T = 1 << 20, F = T / 16;
   float *x, *y; uint16_t* bank; long long* tr;
   cudaMalloc(&x, (size_t)B * T * 4); cudaMalloc(&y, (size_t)B * T * 4); cudaMalloc(&bank, 27 * 4096); cudaMalloc(&tr, (64 * 64 + 512) * 8);
@@ -17,29 +18,28 @@ int main(int argc, char** argv) {
     for (auto& v : hk) v = ((float)rand() / RAND_MAX - 0.5f) * 0.05f;
     for (size_t o = 0; o < (size_t)B * T; o += hx.size()) cudaMemcpy(x + o, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice);
     std::vector<uint16_t> ia(27 * 2048), is(27 * 2048);
-    hankel4_build_banks(hk.data(), 64, 384, ia.data(), is.data());
+    hankel4_build_banks(hk.data(), 16, 512, 64, 384, ia.data(), is.data());
     cudaMemcpy(bank, ia.data(), ia.size() * 2, cudaMemcpyHostToDevice);
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const bool pair = argc > 4 && atoi(argv[4]) != 0;
   H4AnalysisParams p{};
-  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim = argc > 3 ? atoi(argv[3]) : 0;
+  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim = argc > 3 ? atoi(argv[3]) : 0; p.g = h4_shape(16, 64, 384, pair, false);
   for (int rep = 0; rep < 3; ++rep) {
-    int rc = (pair ? h4_launch_analysis<64, 384, true>(p, B, 0) : h4_launch_analysis<64, 384, false>(p, B, 0));
+    int rc = (pair ? h4_launch_analysis<16, true>(p, B, 0) : h4_launch_analysis<16, false>(p, B, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
   }
   const bool synth = argc > 2;
   H4SynthesisParams q{};
-  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim = argc > 3 ? atoi(argv[3]) : 0;
+  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim = argc > 3 ? atoi(argv[3]) : 0; q.g = h4_shape(16, 64, 384, pair, true);
   if (synth) {
     cudaMemset(tr, 0, 64 * 64 * 8);
-    (pair ? h4_launch_synthesis<64, 384, true>(q, B, 0) : h4_launch_synthesis<64, 384, false>(q, B, 0));
+    (pair ? h4_launch_synthesis<16, true>(q, B, 0) : h4_launch_synthesis<16, false>(q, B, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (e) { printf("synthesis cuda=%s\n", cudaGetErrorString(e)); return 1; }
   }
   cudaEventRecord(e0);
-  for (int rep = 0; rep < 20; ++rep) { if (synth) (pair ? h4_launch_synthesis<64, 384, true>(q, B, 0) : h4_launch_synthesis<64, 384, false>(q, B, 0)); else (pair ? h4_launch_analysis<64, 384, true>(p, B, 0) : h4_launch_analysis<64, 384, false>(p, B, 0)); }
+  for (int rep = 0; rep < 20; ++rep) { if (synth) (pair ? h4_launch_synthesis<16, true>(q, B, 0) : h4_launch_synthesis<16, false>(q, B, 0)); else (pair ? h4_launch_analysis<16, true>(p, B, 0) : h4_launch_analysis<16, false>(p, B, 0)); }
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   printf("%s %s data: %.1f us per launch (20 back to back)\n", synth ? "synthesis" : "analysis", argc > 1 ? "random" : "zero", ms * 50.f);

@@ -1,13 +1,13 @@
-// n_band = 16 PQMF, offline fast path: the direct form as an implicit-Hankel GEMM with FOUR frames per operand row.
+// Offline PQMF for n_band 8 / 16 / 32: the direct form as an implicit-Hankel GEMM on the tensor cores, 64 samples per operand row.
 //
 // hankel16.cuh shows that a strided signal can be fed to tcgen05.mma without im2col (one frame = 32 B = the SWIZZLE_32B row
 // pitch), but there every 16 taps cost a full shared-memory read of the 128-row A tile (~111 B/sample: smem-bound at ~30 % of
-// the HBM roofline).  Here one A row holds FOUR frames (64 samples = 128 B in fp16 = the SWIZZLE_128B row pitch) and the
-// bank is replicated at the four frame offsets along N:
-//   analysis : D[i, (delta, k)] = sum_kappa X[64 i + kappa] * hk[k, kappa - 16 delta]      = y[k, frame 4 i + delta]
-//   synthesis: D[i, (delta, p)] = sum_(e,k) S^T[4 i + o - e, k] * 16 hk[k, 16 (e + delta) + p] = out[16 (4 i + delta) + p]
-// so one 128-row MMA (N = 128) yields 512 frames and each signal byte is read from shared memory 4x less often.
-// K-step s reads rows starting at byte 128 (s / 4) + 32 (s % 4).
+// the HBM roofline).  Here one A row holds 64 samples = FR = 64 / M frames (128 B in fp16 = the SWIZZLE_128B row pitch; four
+// frames at n_band 16, hence "Hankel-4") and the bank is replicated at the FR frame offsets along N, so N = FR * M * 2 = 128
+// for every M:
+//   analysis : D[i, (delta, k)] = sum_kappa X[64 i + kappa] * hk[k, kappa - M delta]               = y[k, frame FR i + delta]
+//   synthesis: D[i, (delta, p)] = sum_(e,kb) S^T[FR i + e + n0, kb] * M hk[kb, M (delta + ehi - e) + p] = out[M (FR i + delta) + p]
+// One 128-row MMA group yields 8192 samples; K-step s reads rows starting at byte 32 s of row i (128 (s / 4) + 32 (s % 4)).
 // Precision: the same two-term fp16 split as hankel16.cuh (exact in hk up to 2^-22), columns 0-63 main term, 64-127 the
 // c2 correction; the second pass (h2) uses only the c1 half (N = 64).  Edge K-steps whose correction terms are provably
 // negligible for the actual bank run the main term only (h4_issue_mmas, hankel4_pick_trim).
@@ -26,10 +26,13 @@
 
 namespace pqmf {
 
-constexpr int kH4Workers = 256;                 // convert + drain warps
-constexpr int kH4Threads = kH4Workers + 32;     // + one warp that only issues tcgen05.mma (the issue queue blocks the issuing thread)
-constexpr int kH4Rows = 128;             // A rows per tile
-constexpr int kH4Frames = 4 * kH4Rows;   // 512 frames = 8192 samples per tile
+constexpr int kH4Workers = 256;                 // analysis: convert + drain warps
+constexpr int kH4Threads = kH4Workers + 32;     // + one warp that only issues tcgen05.mma
+constexpr int kH4SynWorkers = 288;              // synthesis: nine worker warps, one (frame quad, band group) item per thread
+constexpr int kH4SynThreads = kH4SynWorkers + 32;
+constexpr int kH4Rows = 128;                    // A rows per tile
+constexpr int kH4TileSamples = 64 * kH4Rows;    // 8192 samples (= 128 FR frames) per tile
+constexpr int kH4MaxPlaneRows = 144;            // register prefetch / item counts are sized for this: K-steps <= 64
 
 // K-major SWIZZLE_128B descriptor: rows 128 B apart, 8-row groups 1024 B apart, 16-byte chunk index ^= address bits 7-9
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -43,66 +46,68 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t byte_lin) { return byte_lin ^ (((byte_lin >> 7) & 7u) << 4); }
 
-// PAIR: the kernel runs as a cluster of two CTAs (tcgen05 cta_group::2).  One M = 256 MMA covers the two CTAs' tiles; each
-// CTA holds only its half of the bank rows: rank 0 [c1 (64 rows) | c1 rows 0-31 again], rank 1 [c2 (64 rows) | c1 rows 32-63],
-// i.e. rows 0-63 are this rank's half of the N = 128 operand and rows 64-95 its half of the N = 64 operand (at the same
-// offset in both CTAs, because one descriptor addresses both).  Per SM and K-step the tensor pipe then reads 6 + 5 KB of
-// operands instead of 8 + 6 KB (experiments/probe_h4_pair.cu: 2380 vs 2868 cycles per tile for the trimmed schedule).
-template <int KT, bool PAIR = false>
-struct H4Geometry {
-  static constexpr int KS = KT / 16 + 3;                        // K-steps: taps + the three extra frame offsets
-  static constexpr int ROWS = kH4Rows + ((KS - 1) >> 2) + 1;    // 128-byte rows of one plane (covers the synthesis pad <= 3 too)
-  static constexpr int PLANE = ((ROWS * 128 + 1023) / 1024) * 1024;
-  static constexpr int BANK_ROWS = PAIR ? 96 : 128;
-  static constexpr int BANK = KS * 2 * BANK_ROWS * 16;          // [2 KS chunks][BANK_ROWS][16 B]
-  static constexpr int OFF_BANK = 0;
-  static constexpr int OFF_P = OFF_BANK + BANK;                 // [2 buffers][h1, h2]
-  static constexpr int OFF_BAR = OFF_P + 4 * PLANE;
-  static constexpr int BYTES = OFF_BAR + 128;
+// Shape of one launch (host and device).  PAIR: the kernel runs as a cluster of two CTAs (tcgen05 cta_group::2).  One M = 256
+// MMA covers the two CTAs' tiles; each CTA holds only its half of the bank rows: rank 0 [c1 (64 rows) | c1 rows 0-31 again],
+// rank 1 [c2 (64 rows) | c1 rows 32-63], i.e. rows 0-63 are this rank's half of the N = 128 operand and rows 64-95 its half of
+// the N = 64 operand (at the same offset in both CTAs, because one descriptor addresses both).  Per SM and K-step the tensor
+// pipe then reads 6 + 5 KB of operands instead of 8 + 6 KB (experiments/probe_h4_pair.cu).
+struct H4Shape {
+  int jlo, kt, ks;     // first non-zero tap, taps kept (multiples of 32), K-steps = ceil((kt + 64 - M) / 16)
+  int rows, plane;     // 128-byte rows of one fp16 plane, bytes per plane (multiple of 1024)
+  int bank;            // bytes of one CTA's bank image: [2 ks chunks][96 or 128 rows][16 B]
+  int bytes;           // dynamic shared memory
 };
+inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
+  H4Shape g;
+  g.jlo = jlo;
+  g.kt = kt;
+  g.ks = (kt + 64 - M + 15) / 16;
+  const int pad_bytes = synthesis ? 3 * 2 * M : 0;               // synthesis shifts its windows by up to 3 frames (alignment)
+  g.rows = kH4Rows + (32 * g.ks + pad_bytes - 1) / 128;
+  g.plane = ((g.rows * 128 + 1023) / 1024) * 1024;
+  g.bank = g.ks * 2 * (pair ? 96 : 128) * 16;
+  g.bytes = g.bank + 4 * g.plane + 128;
+  return g;
+}
+inline bool h4_shape_fits(const H4Shape& g) { return g.rows <= kH4MaxPlaneRows && g.bytes <= 227 * 1024; }
 
 // one elected lane: the MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T.  The first and last `trim`
 // K-steps carry only the tails of the prototype: there the two correction terms (h1 c2, h2 c1) are below the error budget
 // that pqmf_build_tables_f32 checked against the actual bank, so those steps run h1 c1 alone (N = 64) and no h2 pass.
-// `pad` shifts the A windows by whole frames (synthesis alignment).
-template <int KS, bool PAIR>
-__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int pad, int trim) {
+// `pad_bytes` shifts the A windows (synthesis alignment).
+template <bool PAIR>
+__device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int ks,
+                                              int pad_bytes, int trim) {
   constexpr uint32_t kBankRows = PAIR ? 96 : 128;
   const uint64_t da1 = umma_desc_sw128(plane1_addr), da2 = umma_desc_sw128(plane2_addr);
-  const uint64_t db = ptx::umma_desc(bank_addr, kBankRows * 16, 128);                 // N = 128 operand: bank rows from 0
+  const uint64_t db = ptx::umma_desc(bank_addr, kBankRows * 16, 128);                          // N = 128 operand: bank rows from 0
   const uint64_t db64 = PAIR ? ptx::umma_desc(bank_addr + 64 * 16, kBankRows * 16, 128) : db;  // N = 64 operand
   constexpr uint32_t m = PAIR ? 256 : 128;
   constexpr uint32_t idesc128 = ptx::umma_idesc_f16(m, 128), idesc64 = ptx::umma_idesc_f16(m, 64);
-  constexpr uint32_t kStep = 2 * kBankRows;                                          // descriptor units (16 B) per K-step of the bank
-  auto a_step = [&](int s) { return (uint64_t)(8 * ((s + pad) >> 2) + 2 * ((s + pad) & 3)); };  // 128 B per 4 frames, 32 B per frame
+  constexpr uint32_t kStep = 2 * kBankRows;  // descriptor units (16 B) per K-step of the bank
+  auto a_step = [&](int s) {                 // K-step s starts 32 s (+ pad) bytes into row i: 128-byte rows, 16-byte descriptor units
+    const uint32_t byte = 32u * (uint32_t)s + (uint32_t)pad_bytes;
+    return (uint64_t)(8u * (byte >> 7) + ((byte >> 4) & 7u));
+  };
   auto mma = [&](uint64_t a, uint64_t bdesc, uint32_t idesc, bool acc) {
     if constexpr (PAIR) ptx::umma_pair_f16(d_tmem, a, bdesc, idesc, acc);
     else ptx::umma_f16(d_tmem, a, bdesc, idesc, acc);
   };
-  for (int s = trim; s < KS - trim; ++s) mma(da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != trim);
+  for (int s = trim; s < ks - trim; ++s) mma(da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != trim);
   for (int s = 0; s < trim; ++s) {
     mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
-    mma(da1 + a_step(KS - 1 - s), db64 + (uint64_t)(kStep * (KS - 1 - s)), idesc64, true);
+    mma(da1 + a_step(ks - 1 - s), db64 + (uint64_t)(kStep * (ks - 1 - s)), idesc64, true);
   }
-  for (int s = trim; s < KS - trim; ++s) mma(da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = trim; s < ks - trim; ++s) mma(da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
 }
 
-// =============================================================================================
-// analysis
-// =============================================================================================
-struct H4AnalysisParams {
-  const float* x;        // [B, T]
-  float* y;              // [B, 16, F]
-  const uint16_t* bank;  // fp16 image [2 KS][128][8]
-  long T, F;
-  int off;               // 256 (offline only: streaming blocks are far smaller than a tile)
-  int parity;
-  int trim;              // edge K-steps without correction terms (h4_issue_mmas)
-  long tiles_per_row, n_tiles;
-#ifdef PQMF_H4_TRACE
-  long long* trace;      // [iterations][8 warps][8] clock64 stamps of CTA 0 (experiments/trace_h4.cu)
-#endif
-};
+template <int N>
+__device__ __forceinline__ void h4_tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 4 || N == 8 || N == 16, "columns per load");
+  if constexpr (N == 4) ptx::tmem_ld4(taddr, r);
+  else if constexpr (N == 8) ptx::tmem_ld8(taddr, r);
+  else ptx::tmem_ld16(taddr, r);
+}
 
 #ifdef PQMF_H4_TRACE
 #define H4_STAMP(k) do { if (blockIdx.x == 0 && (tid & 31) == 0 && it < 64) p.trace[((size_t)it * 8 + warp) * 8 + (k)] = clock64(); } while (0)
@@ -110,167 +115,258 @@ struct H4AnalysisParams {
 #define H4_STAMP(k) do { } while (0)
 #endif
 
-template <int JLO, int KT, bool PAIR>
-__global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisParams p) {
-  using G = H4Geometry<KT, PAIR>;
-  constexpr int KS = G::KS;
-  constexpr int NQ = (G::ROWS * 16 + kH4Workers - 1) / kH4Workers;  // float4 loads per thread per tile (row = 16 quads)
-  extern __shared__ __align__(1024) unsigned char h4_smem[];
-  unsigned char* smem = h4_smem;
-  unsigned char* bank = smem + G::OFF_BANK;
-  unsigned char* planes = smem + G::OFF_P;
-  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);  // [2]
-  uint64_t* mma_bar = pfull + 2;                                     // [2]
-  uint64_t* bankfull = mma_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bankfull + 1);
+// shared-memory carve-up common to both kernels
+struct H4Smem {
+  unsigned char *bank, *planes;
+  uint64_t *pfull, *mma_bar, *bankfull;
+  uint32_t* tmem_slot;
+};
+__device__ __forceinline__ H4Smem h4_carve(unsigned char* smem, const H4Shape& g) {
+  H4Smem s;
+  s.bank = smem;
+  s.planes = smem + g.bank;
+  s.pfull = reinterpret_cast<uint64_t*>(smem + g.bank + 4 * g.plane);  // [2]
+  s.mma_bar = s.pfull + 2;                                              // [2]
+  s.bankfull = s.mma_bar + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bankfull + 1);
+  return s;
+}
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int kMmaWarp = kH4Workers / 32;
-  // pfull lives in the leader CTA (rank 0): one arrival per worker warp of every CTA of the pair
-  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+// barrier init, TMEM allocation, bank staging.  pfull lives in the leader CTA (rank 0): one arrival per worker warp of every
+// CTA of the pair.  Returns the TMEM base address.
+template <bool PAIR>
+__device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& g, const uint16_t* bank_images, uint32_t rank, int worker_warps,
+                                                int tid) {
+  const int warp = tid >> 5;
   if (tid == 0) {
-    ptx::mbar_init(&pfull[0], (kH4Workers / 32) * (PAIR ? 2 : 1));
-    ptx::mbar_init(&pfull[1], (kH4Workers / 32) * (PAIR ? 2 : 1));
-    ptx::mbar_init(&mma_bar[0], 1);
-    ptx::mbar_init(&mma_bar[1], 1);
-    ptx::mbar_init(bankfull, 1);
+    ptx::mbar_init(&s.pfull[0], worker_warps * (PAIR ? 2 : 1));
+    ptx::mbar_init(&s.pfull[1], worker_warps * (PAIR ? 2 : 1));
+    ptx::mbar_init(&s.mma_bar[0], 1);
+    ptx::mbar_init(&s.mma_bar[1], 1);
+    ptx::mbar_init(s.bankfull, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
     if constexpr (PAIR) {
-      ptx::tmem_alloc_pair(tmem_slot, 256);
+      ptx::tmem_alloc_pair(s.tmem_slot, 256);
     } else {
-      ptx::tmem_alloc(tmem_slot, 256);
+      ptx::tmem_alloc(s.tmem_slot, 256);
       ptx::tmem_relinquish();
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) ptx::cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
+  if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   ptx::tc_fence_after();
-  const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(pfull), 0) : 0u;
-  const uint32_t tmem = *tmem_slot;
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bankfull, G::BANK);
-    ptx::bulk_g2s(bank, reinterpret_cast<const unsigned char*>(p.bank) + (size_t)rank * G::BANK, G::BANK, bankfull);  // PAIR: per-rank images
+    ptx::mbar_arrive_expect_tx(s.bankfull, (uint32_t)g.bank);
+    ptx::bulk_g2s(s.bank, reinterpret_cast<const unsigned char*>(bank_images) + (size_t)rank * g.bank, (uint32_t)g.bank, s.bankfull);
   }
+  return *s.tmem_slot;
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp) {
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (PAIR) {
+    ptx::cluster_sync_all();  // the peer may still be read by / signalled from the leader's last MMAs
+    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
+  } else {
+    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+// the issuer warp's loop (leader CTA only): tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps
+// the issuing thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
+template <bool PAIR>
+__device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g, uint32_t tmem, unsigned n_iter, int pad_bytes, int trim) {
+  const uint32_t bank_addr = ptx::smem_u32(s.bank), plane_addr = ptx::smem_u32(s.planes);
+  for (unsigned it = 0; it < n_iter; ++it) {
+    const int pb = (int)(it & 1);
+    ptx::mbar_wait(&s.pfull[pb], (it >> 1) & 1);
+    ptx::tc_fence_after();
+    if (ptx::elect_one_sync()) {
+      h4_issue_mmas<PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * g.plane, plane_addr + (2 * pb + 1) * g.plane, bank_addr, g.ks,
+                          pad_bytes, trim);
+      if constexpr (PAIR) ptx::umma_pair_commit(&s.mma_bar[pb]);
+      else ptx::umma_commit(&s.mma_bar[pb]);
+    }
+    __syncwarp();
+  }
+}
+
+// a worker warp publishes its share of planes[pb]: one arrival per warp, after this CTA's bank image has landed
+template <bool PAIR>
+__device__ __forceinline__ void h4_publish(const H4Smem& s, uint32_t pfull_leader, unsigned it, int pb, int tid) {
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncwarp();
+  if ((tid & 31) == 0) {
+    if (it == 0) ptx::mbar_wait(s.bankfull, 0);
+    if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
+    else ptx::mbar_arrive(&s.pfull[pb]);
+  }
+}
+
+// =============================================================================================
+// analysis
+// =============================================================================================
+struct H4AnalysisParams {
+  const float* x;        // [B, T]
+  float* y;              // [B, M, F]
+  const uint16_t* bank;  // fp16 image(s), see hankel4_build_banks / hankel4_pair_image
+  long T, F;
+  int off;               // L / 2 (offline only: streaming blocks are far smaller than a tile)
+  int parity;
+  int trim;              // edge K-steps without correction terms (h4_issue_mmas)
+  H4Shape g;
+  long tiles_per_row, n_tiles;
+#ifdef PQMF_H4_TRACE
+  long long* trace;      // [iterations][8 warps][8] clock64 stamps of CTA 0 (experiments/trace_h4.cu)
+#endif
+};
+
+template <int M, bool PAIR>
+__global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisParams p) {
+  constexpr int FR = 64 / M;                                                // frames per 64-sample row
+  constexpr int HB = M / 2;                                                 // bands per epilogue thread
+  constexpr int NQ = (kH4MaxPlaneRows * 16 + kH4Workers - 1) / kH4Workers;  // float4 loads per thread per tile (row = 16 quads)
+  extern __shared__ __align__(1024) unsigned char h4_smem[];
+  const H4Shape g = p.g;
+  const H4Smem sm = h4_carve(h4_smem, g);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int kMmaWarp = kH4Workers / 32;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const uint32_t tmem = h4_prologue<PAIR>(sm, g, p.bank, rank, kH4Workers / 32, tid);
+  const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(sm.pfull), 0) : 0u;
 
   const unsigned tpr = (unsigned)p.tiles_per_row;
   const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
-  const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;   // both CTAs of a pair run the same number of tiles:
+  const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;  // both CTAs of a pair run the same number of tiles:
   const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
-  const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);      // a tile with b >= n_rows is padding (zeros in, nothing out)
+  const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);     // a tile with b >= n_rows is padding (zeros in, nothing out)
 #ifdef PQMF_H4_TRACE
   long long cta_c0 = clock64(), cta_t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
 #endif
 
-  // this thread's share of the fp32 window of one tile (prefetched one tile ahead, straight from global memory)
-  float4 xr[NQ];
-  auto load_window = [&](unsigned bb, unsigned cc) {
-    const long s0 = (long)cc * (kH4Frames * 16) + JLO - p.off;
-    const float* xrow = p.x + (size_t)bb * p.T;
-#pragma unroll
-    for (int r = 0; r < NQ; ++r) {
-      const int q = tid + kH4Workers * r;
-      const long s = s0 + 4L * q;
-      xr[r] = (bb < n_rows && q < G::ROWS * 16 && s >= 0 && s < p.T) ? ptx::ldg128_na(reinterpret_cast<const float4*>(xrow + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  // D (TMEM) -> y: thread (row i, band half hb) owns frames 4 i .. 4 i + 3 of bands 8 hb .. 8 hb + 7: one float4 per band
-  auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
-    const int i = tid & 127, hb = tid >> 7;
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 8 * hb);
-    const long n = (long)cc * kH4Frames + 4 * i;
-    const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
-    float v[4][8];
-#pragma unroll
-    for (int dl = 0; dl < 4; ++dl) {
-      uint32_t r0[8], r1[8];
-      ptx::tmem_ld8(taddr + dl * 16, r0);
-      ptx::tmem_ld8(taddr + 64 + dl * 16, r1);
-      ptx::tmem_ld_wait();
-      // sigma(k, n): odd bands flip on even frames; tiles and 4 i are even, so the frame parity is that of dl (+ p.parity)
-      const uint32_t flip = (((dl + p.parity) & 1) == 0) ? 0x80000000u : 0u;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const float t = (__uint_as_float(r0[kk]) + __uint_as_float(r1[kk])) * scale;
-        v[dl][kk] = __uint_as_float(__float_as_uint(t) ^ ((kk & 1) ? flip : 0u));
-      }
-    }
-    float* yp = p.y + ((size_t)bb * 16 + 8 * hb) * p.F + n;
-    if (n + 3 < p.F && (p.F & 3) == 0) {
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) __stcs(reinterpret_cast<float4*>(yp + (size_t)kk * p.F), make_float4(v[0][kk], v[1][kk], v[2][kk], v[3][kk]));
-    } else {
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-#pragma unroll
-        for (int dl = 0; dl < 4; ++dl)
-          if (n + dl < p.F) yp[(size_t)kk * p.F + dl] = v[dl][kk];
-    }
-  };
-
-  const uint32_t bank_addr = ptx::smem_u32(bank), plane_addr = ptx::smem_u32(planes);
   if (warp == kMmaWarp) {
-    // ---- issuer warp: tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps the issuing
-    //      thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
-    for (unsigned it = 0; rank == 0 && it < n_iter; ++it) {
-      const int pb = (int)(it & 1);
-      ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS, PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, 0, p.trim);
-        if constexpr (PAIR) ptx::umma_pair_commit(&mma_bar[pb]);
-        else ptx::umma_commit(&mma_bar[pb]);
-      }
-      __syncwarp();
-    }
+    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim);
   } else {
-    load_window(b, c);
+    const int n_quads = g.rows * 16;
+    // this thread's share of the fp32 window of a tile, prefetched TWO tiles ahead straight from global memory into two register
+    // sets (with one tile of prefetch the DRAM latency of the loads was exposed every iteration once the tensor pipe was no
+    // longer the bottleneck: n_band 8 needs 16 K-steps per tile and ran no faster than n_band 16 with 27)
+    float4 x0[NQ], x1[NQ];
+    auto load_window = [&](float4 (&xr)[NQ], unsigned bb, unsigned cc) {
+      const long s0 = (long)cc * kH4TileSamples + g.jlo - p.off;
+      const float* xrow = p.x + (size_t)bb * p.T;
+#pragma unroll
+      for (int r = 0; r < NQ; ++r) {
+        const int q = tid + kH4Workers * r;
+        const long s = s0 + 4L * q;
+        xr[r] = (bb < n_rows && q < n_quads && s >= 0 && s < p.T) ? ptx::ldg128_na(reinterpret_cast<const float4*>(xrow + s))
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    // fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples).  planes[pb] were last read by the MMAs of tile it-2,
+    // whose completion this thread observed before draining tile it-2.
+    auto convert = [&](const float4 (&xr)[NQ], int pb) {
+      unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
+      unsigned char* p2 = p1 + g.plane;
+#pragma unroll
+      for (int r = 0; r < NQ; ++r) {
+        const int q = tid + kH4Workers * r;
+        if (q < n_quads) {
+          uint2 a, bq;
+          split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
+          split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
+          const uint32_t o = sw128_offset((uint32_t)q * 8u);
+          *reinterpret_cast<uint2*>(p1 + o) = a;
+          *reinterpret_cast<uint2*>(p2 + o) = bq;
+        }
+      }
+    };
+    auto advance = [&](unsigned& bb, unsigned& cc) {
+      bb += step_b;
+      cc += step_c;
+      if (cc >= tpr) {
+        cc -= tpr;
+        ++bb;
+      }
+    };
+    // D (TMEM) -> y: thread (row i, band half hb) owns frames FR i .. FR i + FR - 1 of bands HB hb .. HB hb + HB - 1:
+    // FR consecutive frames per band (32 / 16 / 8 bytes at n_band 8 / 16 / 32), consecutive rows in consecutive lanes
+    auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
+      const int i = tid & 127, hb = tid >> 7;
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + HB * hb);
+      const long n = ((long)cc * kH4Rows + i) * FR;
+      const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
+      uint32_t r0[FR][HB], r1[FR][HB];
+#pragma unroll
+      for (int dl = 0; dl < FR; ++dl) {
+        h4_tmem_ld<HB>(taddr + dl * M, r0[dl]);
+        h4_tmem_ld<HB>(taddr + 64 + dl * M, r1[dl]);
+      }
+      ptx::tmem_ld_wait();
+      float v[FR][HB];
+#pragma unroll
+      for (int dl = 0; dl < FR; ++dl) {
+        // sigma(k, n): odd bands flip on even frames; n (a multiple of FR) is even for FR > 1, so the frame parity is dl's
+        const uint32_t flip = (((FR > 1 ? dl : (int)(n & 1)) + p.parity) & 1) == 0 ? 0x80000000u : 0u;
+#pragma unroll
+        for (int kk = 0; kk < HB; ++kk) {
+          const float t = (__uint_as_float(r0[dl][kk]) + __uint_as_float(r1[dl][kk])) * scale;
+          v[dl][kk] = __uint_as_float(__float_as_uint(t) ^ ((kk & 1) ? flip : 0u));
+        }
+      }
+      float* yp = p.y + ((size_t)bb * M + HB * hb) * p.F + n;
+      if (n + FR - 1 < p.F && (p.F % (FR >= 4 ? 4 : FR)) == 0) {
+#pragma unroll
+        for (int kk = 0; kk < HB; ++kk) {
+          float* q = yp + (size_t)kk * p.F;
+          if constexpr (FR >= 4) {
+#pragma unroll
+            for (int d4 = 0; d4 < FR; d4 += 4) __stcs(reinterpret_cast<float4*>(q + d4), make_float4(v[d4][kk], v[d4 + 1][kk], v[d4 + 2][kk], v[d4 + 3][kk]));
+          } else if constexpr (FR == 2) {
+            __stcs(reinterpret_cast<float2*>(q), make_float2(v[0][kk], v[1][kk]));
+          } else {
+            __stcs(q, v[0][kk]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < HB; ++kk)
+#pragma unroll
+          for (int dl = 0; dl < FR; ++dl)
+            if (n + dl < p.F) yp[(size_t)kk * p.F + dl] = v[dl][kk];
+      }
+    };
+
+    unsigned b1 = b, c1 = c;  // tile it + 1
+    advance(b1, c1);
+    unsigned b2 = b1, c2 = c1;  // tile it + 2
+    advance(b2, c2);
+    load_window(x0, b, c);
+    if (n_iter > 1) load_window(x1, b1, c1);
     unsigned prev_b = 0, prev_c = 0;
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       H4_STAMP(0);
-      // ---- fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples).  planes[pb] were last read by the MMAs of
-      //      tile it-2, whose completion this thread observed before draining tile it-2.
-      {
-        unsigned char* p1 = planes + (2 * pb) * G::PLANE;
-        unsigned char* p2 = p1 + G::PLANE;
-#pragma unroll
-        for (int r = 0; r < NQ; ++r) {
-          const int q = tid + kH4Workers * r;
-          if (q < G::ROWS * 16) {
-            uint2 a, bq;
-            split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
-            split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
-            const uint32_t o = sw128_offset((uint32_t)q * 8u);
-            *reinterpret_cast<uint2*>(p1 + o) = a;
-            *reinterpret_cast<uint2*>(p2 + o) = bq;
-          }
-        }
-      }
+      if (it & 1) convert(x1, pb);
+      else convert(x0, pb);
       H4_STAMP(1);
-      ptx::fence_proxy_async();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if ((tid & 31) == 0) {
-        if (it == 0) ptx::mbar_wait(bankfull, 0);   // this CTA's bank image has landed before its first arrival
-        if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
-        else ptx::mbar_arrive(&pfull[pb]);
+      h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
+      if (it + 2 < n_iter) {  // refill the register set that was just consumed
+        if (it & 1) load_window(x1, b2, c2);
+        else load_window(x0, b2, c2);
       }
-      // prefetch the next tile's window (consumed at the top of the next iteration)
-      unsigned nb = b + step_b, nc = c + step_c;
-      if (nc >= tpr) {
-        nc -= tpr;
-        ++nb;
-      }
-      if (it + 1 < n_iter) load_window(nb, nc);
       H4_STAMP(2);
       H4_STAMP(3);
       if (it > 0) {
-        ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
         ptx::tc_fence_after();
         H4_STAMP(4);
         if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
@@ -278,16 +374,18 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       H4_STAMP(5);
       prev_b = b;
       prev_c = c;
-      b = nb;
-      c = nc;
+      b = b1;
+      c = c1;
+      b1 = b2;
+      c1 = c2;
+      advance(b2, c2);
     }
-    ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
     ptx::tc_fence_after();
     if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
-  ptx::tc_fence_before();
-  __syncthreads();
 #ifdef PQMF_H4_TRACE
+  __syncthreads();
   if (tid == 0) {
     long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -295,123 +393,105 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     p.trace[64 * 64 + 2 * blockIdx.x + 1] = t1 - cta_t0;
   }
 #endif
-  if constexpr (PAIR) {
-    ptx::cluster_sync_all();   // the peer may still be read by / signalled from the leader's last MMAs
-    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
-  } else {
-    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
-  }
+  h4_teardown<PAIR>(tmem, warp);
 }
 
 // =============================================================================================
 // synthesis
 // =============================================================================================
 struct H4SynthesisParams {
-  const float* s;        // [B, 16, F]
-  float* out;            // [B, 16 F]
+  const float* s;        // [B, M, F]
+  float* out;            // [B, M F]
   const uint16_t* bank;
   long F;
-  int o;                 // off2 / 16: 16 (PQMF.inverse) or 15 (CachedPQMF.inverse)
+  int o;                 // off2 / M: L / (2 M) (PQMF.inverse) or one less (CachedPQMF.inverse)
   int parity;
   int trim;
+  H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
   long long* trace;
 #endif
 };
 
-constexpr int kH4SynWorkers = 288;                    // nine worker warps: 2 x ROWS (<= 274) load/convert items, one per thread
-constexpr int kH4SynThreads = kH4SynWorkers + 32;     // + the issuer warp
-
-template <int JLO, int KT, bool PAIR>
+template <int M, bool PAIR>
 __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
-  using G = H4Geometry<KT, PAIR>;
-  constexpr int KS = G::KS;
-  constexpr int EHI = (JLO + KT) / 16 - 1;        // largest frame lag with a non-zero tap
-  static_assert(2 * G::ROWS <= kH4SynWorkers, "one (frame quad, band half) item per worker thread");
+  constexpr int FR = 64 / M;       // frames per 128-byte plane row ([frame][band] fp16)
+  constexpr int NBG = M / 8;       // band groups of 8 (one 16-byte chunk per frame)
   extern __shared__ __align__(1024) unsigned char h4s_smem[];
-  unsigned char* smem = h4s_smem;
-  unsigned char* bank = smem + G::OFF_BANK;
-  unsigned char* planes = smem + G::OFF_P;
-  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
-  uint64_t* mma_bar = pfull + 2;
-  uint64_t* bankfull = mma_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bankfull + 1);
-
+  const H4Shape g = p.g;
+  const H4Smem sm = h4_carve(h4s_smem, g);
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int kMmaWarp = kH4SynWorkers / 32;
-  // pfull lives in the leader CTA (rank 0): one arrival per worker warp of every CTA of the pair
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
-  if (tid == 0) {
-    ptx::mbar_init(&pfull[0], (kH4SynWorkers / 32) * (PAIR ? 2 : 1));
-    ptx::mbar_init(&pfull[1], (kH4SynWorkers / 32) * (PAIR ? 2 : 1));
-    ptx::mbar_init(&mma_bar[0], 1);
-    ptx::mbar_init(&mma_bar[1], 1);
-    ptx::mbar_init(bankfull, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 0) {
-    if constexpr (PAIR) {
-      ptx::tmem_alloc_pair(tmem_slot, 256);
-    } else {
-      ptx::tmem_alloc(tmem_slot, 256);
-      ptx::tmem_relinquish();
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if constexpr (PAIR) ptx::cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
-  ptx::tc_fence_after();
-  const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(pfull), 0) : 0u;
-  const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bankfull, G::BANK);
-    ptx::bulk_g2s(bank, reinterpret_cast<const unsigned char*>(p.bank) + (size_t)rank * G::BANK, G::BANK, bankfull);  // PAIR: per-rank images
-  }
+  const uint32_t tmem = h4_prologue<PAIR>(sm, g, p.bank, rank, kH4SynWorkers / 32, tid);
+  const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(sm.pfull), 0) : 0u;
 
   const unsigned tpr = (unsigned)p.tiles_per_row;
   const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
-  const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;   // both CTAs of a pair run the same number of tiles:
+  const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;
   const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
-  const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);      // a tile with b >= n_rows is padding (zeros in, nothing out)
+  const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);
 
-  // plane frame m <-> sub-band frame n = 512 c + (o - EHI - pad) + m, pad = (o - EHI) mod 4, so that frame quads are
-  // 16-byte aligned in global memory; K-step s of row i then reads plane frame 4 i + s + pad.
-  const int pad = (p.o - EHI) & 3;
-  const int nbase = p.o - EHI - pad;              // multiple of 4 (may be negative)
-  const uint32_t bank_addr = ptx::smem_u32(bank), plane_addr = ptx::smem_u32(planes);
+  // plane frame m <-> sub-band frame n = 128 FR c + (o - ehi - pad) + m, ehi = largest frame lag with a non-zero tap,
+  // pad = (o - ehi) mod 4, so that frame quads are 16-byte aligned in global memory; K-step s of row i then starts
+  // 32 s + 2 M pad bytes into the row.
+  const int ehi = (g.jlo + g.kt) / M - 1;
+  const int pad = (p.o - ehi) & 3;
+  const int nbase = p.o - ehi - pad;  // multiple of 4 (may be negative)
   if (warp == kMmaWarp) {
-    // ---- issuer warp (see the analysis kernel)
-    for (unsigned it = 0; rank == 0 && it < n_iter; ++it) {
-      const int pb = (int)(it & 1);
-      ptx::mbar_wait(&pfull[pb], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      if (ptx::elect_one_sync()) {
-        h4_issue_mmas<KS, PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * G::PLANE, plane_addr + (2 * pb + 1) * G::PLANE, bank_addr, pad, p.trim);
-        if constexpr (PAIR) ptx::umma_pair_commit(&mma_bar[pb]);
-        else ptx::umma_commit(&mma_bar[pb]);
-      }
-      __syncwarp();
-    }
+    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 2 * M * pad, p.trim);
   } else {
-    // ---- workers.  Item (m4, ch): frames 4 m4 .. 4 m4 + 3 of bands 8 ch .. 8 ch + 7 = eight float4 loads (prefetched one
-    //      tile ahead) -> four 16-byte chunks per fp16 plane.  ch-major thread order keeps a quarter-warp on eight
-    //      consecutive rows, whose SWIZZLE_128B images of one chunk column hit eight different bank groups.
-    const int ch = tid >= G::ROWS ? 1 : 0, m4 = tid - ch * G::ROWS;
-    const bool has_item = tid < 2 * G::ROWS;
-    float4 v[8];
-    auto load_frames = [&](unsigned bb, unsigned cc) {
-      const long n = (long)cc * kH4Frames + nbase + 4 * m4;
-      const float* sp = p.s + ((size_t)bb * 16 + 8 * ch) * p.F + n;
+    // ---- workers.  Item (fq, bg): frames 4 fq .. 4 fq + 3 of bands 8 bg .. 8 bg + 7 = eight float4 loads (prefetched one
+    //      tile ahead) -> four 16-byte chunks per fp16 plane.  bg-major thread order keeps a quarter-warp on eight consecutive
+    //      frame quads of one band group: their SWIZZLE_128B images hit eight different bank groups at n_band 8 and 16.
+    const int n_fq = g.rows * FR / 4;                        // frame quads per plane
+    const int bg = tid / n_fq, fq = tid - bg * n_fq;
+    const bool has_item = tid < n_fq * NBG;
+    float4 v0[8], v1[8];  // two register sets: loads run two tiles ahead (see the analysis kernel)
+    auto load_frames = [&](float4 (&v)[8], unsigned bb, unsigned cc) {
+      const long n = (long)cc * (kH4Rows * FR) + nbase + 4 * fq;
+      const float* sp = p.s + ((size_t)bb * M + 8 * bg) * p.F + n;
       const bool ok = bb < n_rows && has_item && n >= 0 && n + 3 < p.F;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // D (TMEM) -> out.  Thread (row i, half hb) drains output frames 4 i + 2 hb, + 1 = 32 consecutive samples = four 32-byte
-    // chunks, but rows are 256 B apart: stored like that, every warp store would touch 32 lines.  A 4 x 4 chunk transpose
-    // inside each lane quad (two shuffle stages) leaves lane r with chunk r & 3 of the quad's four rows, so one STG.256
-    // covers eight whole 128-byte lines.
+    // sigma(k, n): odd bands (odd kk) flip on even global frames; quads start on multiples of 4, so the parity is j's
+    const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
+    auto convert = [&](const float4 (&v)[8], int pb) {
+      if (!has_item) return;
+      unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t fl = (j & 1) ? flip_odd : flip_even;
+        float w[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const float t = j == 0 ? v[kk].x : j == 1 ? v[kk].y : j == 2 ? v[kk].z : v[kk].w;
+          w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
+        }
+        uint4 h1, h2;
+        split2_f16(w[0], w[1], h1.x, h2.x);
+        split2_f16(w[2], w[3], h1.y, h2.y);
+        split2_f16(w[4], w[5], h1.z, h2.z);
+        split2_f16(w[6], w[7], h1.w, h2.w);
+        const uint32_t o = sw128_offset((uint32_t)(4 * fq + j) * (2u * M) + 16u * bg);  // frame 4 fq + j, bands 8 bg .. 8 bg + 7
+        *reinterpret_cast<uint4*>(p1 + o) = h1;
+        *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
+      }
+    };
+    auto advance = [&](unsigned& bb, unsigned& cc) {
+      bb += step_b;
+      cc += step_c;
+      if (cc >= tpr) {
+        cc -= tpr;
+        ++bb;
+      }
+    };
+    // D (TMEM) -> out.  Thread (row i, half hb) drains 32 consecutive output samples = four 32-byte chunks, but rows are 256 B
+    // apart: stored like that, every warp store would touch 32 lines.  A 4 x 4 chunk transpose inside each lane quad (two shuffle
+    // stages) leaves lane r with chunk r & 3 of the quad's four rows, so one STG.256 covers eight whole 128-byte lines.
     auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
       const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
       const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
@@ -422,14 +502,14 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       ptx::tmem_ld16(taddr + 16, r0[1]);
       ptx::tmem_ld16(taddr + 80, r1[1]);
       ptx::tmem_ld_wait();
-      float val[4][8];   // chunk q = 2 dd + c8
+      float val[4][8];  // chunk q = samples 32 hb + 8 q .. + 7 of the row
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int e = 0; e < 8; ++e) val[q][e] = (__uint_as_float(r0[q >> 1][8 * (q & 1) + e]) + __uint_as_float(r1[q >> 1][8 * (q & 1) + e])) * scale;
       const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
-      for (int pr = 0; pr < 2; ++pr)   // lanes r, r ^ 1 swap the off-diagonal chunks of (2 pr, 2 pr + 1)
+      for (int pr = 0; pr < 2; ++pr)  // lanes r, r ^ 1 swap the off-diagonal chunks of (2 pr, 2 pr + 1)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float recv = __shfl_xor_sync(0xffffffffu, b0 ? val[2 * pr][e] : val[2 * pr + 1][e], 1);
@@ -437,70 +517,45 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
           val[2 * pr][e] = b0 ? recv : val[2 * pr][e];
         }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)      // lanes r, r ^ 2 swap the off-diagonal chunks of (u, u + 2)
+      for (int u = 0; u < 2; ++u)  // lanes r, r ^ 2 swap the off-diagonal chunks of (u, u + 2)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float recv = __shfl_xor_sync(0xffffffffu, b1 ? val[u][e] : val[u + 2][e], 2);
           val[u + 2][e] = b1 ? val[u + 2][e] : recv;
           val[u][e] = b1 ? recv : val[u][e];
         }
-      // slot q now holds chunk (lane & 3) of row (i & ~3) | q
-      const int cq = lane & 3;
-      const long f0 = (long)cc * kH4Frames + 4 * (i & ~3) + 2 * hb + (cq >> 1);
-      float* op = p.out + ((size_t)bb * p.F + f0) * 16 + 8 * (cq & 1);
+      // slot q now holds chunk (lane & 3) of row (i & ~3) | q: samples 64 row + 32 hb + 8 (lane & 3) .. + 7 of the tile
+      const long total = p.F * M;  // samples per output row (a multiple of 8: the dispatcher requires F % 4 == 0)
+      const long t0 = (long)cc * kH4TileSamples + 64 * (i & ~3) + 32 * hb + 8 * (lane & 3);
+      float* op = p.out + (size_t)bb * total + t0;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (f0 + 4 * q < p.F) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
+        if (t0 + 64 * q + 7 < total) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
     };
 
-    load_frames(b, c);
+    unsigned b1 = b, c1 = c;
+    advance(b1, c1);
+    unsigned b2 = b1, c2 = c1;
+    advance(b2, c2);
+    load_frames(v0, b, c);
+    if (n_iter > 1) load_frames(v1, b1, c1);
     unsigned prev_b = 0, prev_c = 0;
-    // sigma(k, n): odd bands (odd kk) flip on even global frames; quads start on multiples of 4, so the parity is j's
-    const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       H4_STAMP(0);
-      if (has_item) {
-        unsigned char* p1 = planes + (2 * pb) * G::PLANE;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t fl = (j & 1) ? flip_odd : flip_even;
-          float w[8];
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const float t = j == 0 ? v[kk].x : j == 1 ? v[kk].y : j == 2 ? v[kk].z : v[kk].w;
-            w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
-          }
-          uint4 h1, h2;
-          split2_f16(w[0], w[1], h1.x, h2.x);
-          split2_f16(w[2], w[3], h1.y, h2.y);
-          split2_f16(w[4], w[5], h1.z, h2.z);
-          split2_f16(w[6], w[7], h1.w, h2.w);
-          const uint32_t o = sw128_offset((uint32_t)m4 * 128u + 32u * j + 16u * ch);
-          *reinterpret_cast<uint4*>(p1 + o) = h1;
-          *reinterpret_cast<uint4*>(p1 + G::PLANE + o) = h2;
-        }
-      }
+      if (it & 1) convert(v1, pb);
+      else convert(v0, pb);
       H4_STAMP(1);
-      ptx::fence_proxy_async();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if ((tid & 31) == 0) {
-        if (it == 0) ptx::mbar_wait(bankfull, 0);
-        if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
-        else ptx::mbar_arrive(&pfull[pb]);
+      h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
+      if (it + 2 < n_iter) {
+        if (it & 1) load_frames(v1, b2, c2);
+        else load_frames(v0, b2, c2);
       }
-      unsigned nb = b + step_b, nc = c + step_c;
-      if (nc >= tpr) {
-        nc -= tpr;
-        ++nb;
-      }
-      if (it + 1 < n_iter) load_frames(nb, nc);
       H4_STAMP(2);
       H4_STAMP(3);
       if (it > 0) {
         // every worker waits (planes[pb ^ 1] are rewritten next iteration); the ninth warp has no TMEM rows to drain
-        ptx::mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
         ptx::tc_fence_after();
         H4_STAMP(4);
         if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
@@ -508,28 +563,24 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       H4_STAMP(5);
       prev_b = b;
       prev_c = c;
-      b = nb;
-      c = nc;
+      b = b1;
+      c = c1;
+      b1 = b2;
+      c1 = c2;
+      advance(b2, c2);
     }
-    ptx::mbar_wait(&mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
     ptx::tc_fence_after();
     if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
-  ptx::tc_fence_before();
-  __syncthreads();
-  if constexpr (PAIR) {
-    ptx::cluster_sync_all();   // the peer may still be read by / signalled from the leader's last MMAs
-    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
-  } else {
-    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
-  }
+  h4_teardown<PAIR>(tmem, warp);
 }
 
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
 template <typename Kern>
-inline int h4_configure(Kern kern, int bytes, bool (&configured)[64], int& sm_count_out) {
+inline int h4_configure(Kern kern, int bytes, int (&configured)[64], int& sm_count_out) {
   static int sm_count[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -539,10 +590,10 @@ inline int h4_configure(Kern kern, int bytes, bool (&configured)[64], int& sm_co
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sm_count[dev] = n > 0 ? n : 148;
   }
-  if (!configured[dev]) {
+  if (configured[dev] < bytes) {  // the opt-in limit only ever grows (shapes with more K-steps need more shared memory)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return (int)e;
-    configured[dev] = true;
+    configured[dev] = bytes;
   }
   sm_count_out = sm_count[dev];
   return 0;
@@ -550,10 +601,11 @@ inline int h4_configure(Kern kern, int bytes, bool (&configured)[64], int& sm_co
 
 // one CTA (or CTA pair) per SM, static round-robin over the tiles; PAIR launches clusters of two
 template <bool PAIR, typename Kern, typename Params>
-inline int h4_launch(Kern kern, Params p, int B, int threads, int bytes, bool (&configured)[64], cudaStream_t st) {
+inline int h4_launch(Kern kern, Params p, int B, long row_samples, int threads, int (&configured)[64], cudaStream_t st) {
   int sms = 0;
-  if (int e = h4_configure(kern, bytes, configured, sms)) return e;
-  p.tiles_per_row = (p.F + kH4Frames - 1) / kH4Frames;
+  if (!h4_shape_fits(p.g)) return -2;
+  if (int e = h4_configure(kern, p.g.bytes, configured, sms)) return e;
+  p.tiles_per_row = (row_samples + kH4TileSamples - 1) / kH4TileSamples;
   p.n_tiles = p.tiles_per_row * B;
   if (p.tiles_per_row >= (1L << 31) || p.n_tiles >= (1L << 40)) return -2;
   long grid = PAIR ? (sms & ~1) : sms;
@@ -563,7 +615,7 @@ inline int h4_launch(Kern kern, Params p, int B, int threads, int bytes, bool (&
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = (size_t)bytes;
+    cfg.dynamicSmemBytes = (size_t)p.g.bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -574,52 +626,52 @@ inline int h4_launch(Kern kern, Params p, int B, int threads, int bytes, bool (&
     cfg.numAttrs = 1;
     return (int)cudaLaunchKernelEx(&cfg, kern, p);
   } else {
-    kern<<<(unsigned)grid, threads, bytes, st>>>(p);
+    kern<<<(unsigned)grid, threads, p.g.bytes, st>>>(p);
     return (int)cudaGetLastError();
   }
 }
 
-template <int JLO, int KT, bool PAIR = false>
+template <int M, bool PAIR>
 int h4_launch_analysis(H4AnalysisParams p, int B, cudaStream_t st) {
-  static bool configured[64] = {false};
-  return h4_launch<PAIR>(h4_analysis_kernel<JLO, KT, PAIR>, p, B, kH4Threads, H4Geometry<KT, PAIR>::BYTES, configured, st);
+  static int configured[64] = {0};
+  return h4_launch<PAIR>(h4_analysis_kernel<M, PAIR>, p, B, p.F * M, kH4Threads, configured, st);
 }
 
-template <int JLO, int KT, bool PAIR = false>
+template <int M, bool PAIR>
 int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
-  static bool configured[64] = {false};
-  return h4_launch<PAIR>(h4_synthesis_kernel<JLO, KT, PAIR>, p, B, kH4SynThreads, H4Geometry<KT, PAIR>::BYTES, configured, st);
+  static int configured[64] = {0};
+  return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR>, p, B, p.F * M, kH4SynThreads, configured, st);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host: bank images, fp16 bits in UMMA K-major no-swizzle layout [chunk of 8 K][128 rows][8],
-// rows = part * 64 + delta * 16 + (band | phase), part 0 = c1, part 1 = c2
+// rows = part * 64 + delta * M + (band | phase), part 0 = c1, part 1 = c2
 // ---------------------------------------------------------------------------------------------
-inline void hankel4_build_banks(const float* hk /*[16][512]*/, int jlo, int kt, uint16_t* img_analysis, uint16_t* img_synthesis) {
+inline void hankel4_build_banks(const float* hk /*[M][L]*/, int M, int L, int jlo, int kt, uint16_t* img_analysis, uint16_t* img_synthesis) {
   auto bits = [](float v) {
     const __half h = __float2half_rn(v);
     uint16_t u;
     memcpy(&u, &h, 2);
     return u;
   };
-  const int ks = kt / 16 + 3, kp = 16 * ks;
-  const int dlo = jlo / 16, dhi = (jlo + kt) / 16 - 1;
-  const float sa = (float)(1 << kH16ScaleLog2), ss = 16.f * sa;
+  const int ks = (kt + 64 - M + 15) / 16, kp = 16 * ks;
+  const int elo = jlo / M, ehi = (jlo + kt) / M - 1;
+  const float sa = (float)(1 << kH16ScaleLog2), ss = (float)M * sa;
   for (int kc = 0; kc < kp / 8; ++kc)
     for (int row = 0; row < 128; ++row)
-      for (int e = 0; e < 8; ++e) {
-        const int kap = 8 * kc + e;
-        const int part = row / 64, delta = (row % 64) / 16, q = row % 16;
-        const size_t at = ((size_t)kc * 128 + row) * 8 + e;
+      for (int e8 = 0; e8 < 8; ++e8) {
+        const int kap = 8 * kc + e8;
+        const int part = row / 64, delta = (row % 64) / M, q = row % M;
+        const size_t at = ((size_t)kc * 128 + row) * 8 + e8;
         {  // analysis: K index = tap offset within the (delta-shifted) window, q = band
-          const int j = kap - 16 * delta;
-          const float v = (j >= 0 && j < kt) ? sa * hk[q * 512 + jlo + j] : 0.f;
+          const int j = kap - M * delta;
+          const float v = (j >= 0 && j < kt) ? sa * hk[(size_t)q * L + jlo + j] : 0.f;
           const float c1 = __half2float(__float2half_rn(v));
           img_analysis[at] = part == 0 ? bits(c1) : bits(v - c1);
         }
-        {  // synthesis: K index = (step s, band kb): lag e = dhi - s, tap 16 (e + delta) + q, q = output phase
-          const int s2 = kap / 16, kb = kap % 16, d = dhi - s2 + delta;
-          const float v = (d >= dlo && d <= dhi) ? ss * hk[kb * 512 + 16 * d + q] : 0.f;
+        {  // synthesis: K index = (frame e, band kb) of the [frame][band] plane: lag = delta + ehi - e, tap M lag + q, q = output phase
+          const int e = kap / M, kb = kap % M, lag = delta + ehi - e;
+          const float v = (lag >= elo && lag <= ehi) ? ss * hk[(size_t)kb * L + M * lag + q] : 0.f;
           const float c1 = __half2float(__float2half_rn(v));
           img_synthesis[at] = part == 0 ? bits(c1) : bits(v - c1);
         }
@@ -628,8 +680,8 @@ inline void hankel4_build_banks(const float* hk /*[16][512]*/, int jlo, int kt, 
 
 // per-rank images for the CTA-pair kernels: [rank][2 KS][96 rows][8]; rows 0-63 = rows 64 rank .. of the single-CTA image (rank 0:
 // c1, rank 1: c2), rows 64-95 = c1 rows 32 rank .. 32 rank + 31 (this rank's half of the N = 64 operand)
-inline void hankel4_pair_image(const uint16_t* single /*[2 KS][128][8]*/, int kt, uint16_t* pair /*[2][2 KS][96][8]*/) {
-  const int chunks = 2 * (kt / 16 + 3);
+inline void hankel4_pair_image(const uint16_t* single /*[2 KS][128][8]*/, int ks, uint16_t* pair /*[2][2 KS][96][8]*/) {
+  const int chunks = 2 * ks;
   for (int r = 0; r < 2; ++r)
     for (int kc = 0; kc < chunks; ++kc)
       for (int row = 0; row < 96; ++row) {
@@ -640,26 +692,26 @@ inline void hankel4_pair_image(const uint16_t* single /*[2 KS][128][8]*/, int kt
 
 // Largest number of edge K-steps (per side, <= 7) whose correction terms may be dropped: the dropped terms are bounded by
 // 2 * 2^-11 * max|input| * (sum of the |bank| entries they multiply); returns the largest trim whose bound stays <= budget.
-inline int hankel4_pick_trim(const float* hk /*[16][512]*/, int jlo, int kt, bool synthesis, double budget) {
-  const int ks = kt / 16 + 3, dlo = jlo / 16, dhi = (jlo + kt) / 16 - 1;
+inline int hankel4_pick_trim(const float* hk /*[M][L]*/, int M, int L, int jlo, int kt, bool synthesis, double budget) {
+  const int ks = (kt + 64 - M + 15) / 16, fr = 64 / M, elo = jlo / M, ehi = (jlo + kt) / M - 1;
   int best = 0;
   for (int trim = 1; trim <= 7 && ks - 2 * trim >= 1; ++trim) {
     double worst = 0.0;
-    for (int delta = 0; delta < 4; ++delta)
-      for (int q = 0; q < 16; ++q) {   // q = band (analysis) or output phase (synthesis)
+    for (int delta = 0; delta < fr; ++delta)
+      for (int q = 0; q < M; ++q) {  // q = band (analysis) or output phase (synthesis)
         double sum = 0.0;
         for (int side = 0; side < 2; ++side)
           for (int t = 0; t < trim; ++t) {
             const int s = side ? ks - 1 - t : t;
-            if (!synthesis) {
-              for (int e = 0; e < 16; ++e) {
-                const int j = 16 * s + e - 16 * delta;
-                if (j >= 0 && j < kt) sum += fabs((double)hk[q * 512 + jlo + j]);
+            for (int e16 = 0; e16 < 16; ++e16) {
+              const int kap = 16 * s + e16;
+              if (!synthesis) {
+                const int j = kap - M * delta;
+                if (j >= 0 && j < kt) sum += fabs((double)hk[(size_t)q * L + jlo + j]);
+              } else {
+                const int e = kap / M, kb = kap % M, lag = delta + ehi - e;
+                if (lag >= elo && lag <= ehi) sum += (double)M * fabs((double)hk[(size_t)kb * L + M * lag + q]);
               }
-            } else {
-              const int d = dhi - s + delta;
-              if (d >= dlo && d <= dhi)
-                for (int k = 0; k < 16; ++k) sum += 16.0 * fabs((double)hk[k * 512 + 16 * d + q]);
             }
           }
         worst = sum > worst ? sum : worst;

@@ -141,33 +141,85 @@ constexpr long kH4ImageFloats = 35L * 4096 / 4;        // one hankel4 bank image
 constexpr long kH4PairOffset = kH4TableOffset + 2 * kH4ImageFloats;
 constexpr long kH4PairImageFloats = 2L * 35 * 3072 / 4;  // per-rank images of the CTA-pair kernels (fp16 [2][2 KS][96][8])
 
-// offline n_band 16 default: four-frames-per-row Hankel GEMM (hankel4.cuh) when there are enough 512-frame tiles
-bool use_h4(int B, long F, const float* hist) { return hist == nullptr && (long)B * ((F + 511) / 512) >= 96; }
-int h4_analysis(const float* x, float* y, const float* tables, int B, long T, long F, int off, unsigned flags, cudaStream_t st) {
-  const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
-  pqmf::H4AnalysisParams p{};
-  p.x = x; p.y = y; p.T = T; p.F = F; p.off = off; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
-  if (!(flags & PQMF_FLAG_NO_PAIR)) {
-    p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset);
-    const int e = trimmed ? pqmf::h4_launch_analysis<64, 384, true>(p, B, st) : pqmf::h4_launch_analysis<0, 512, true>(p, B, st);
-    if (e == 0) return 0;
-    (void)cudaGetLastError();   // a context that cannot co-schedule CTA pairs (e.g. an SM partition): same arithmetic, one CTA per SM
-  }
-  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
-  return trimmed ? pqmf::h4_launch_analysis<64, 384>(p, B, st) : pqmf::h4_launch_analysis<0, 512>(p, B, st);
+// ---- offline default for n_band 8 / 16 / 32: the 64-samples-per-row Hankel GEMM (hankel4.cuh) when there are enough tiles ----
+bool h4_family(int M, int L) { return (M == 8 || M == 16 || M == 32) && L == 32 * M; }
+long h4_pair_floats(int M, int L) { return 1536L * ((L + 64 - M + 15) / 16); }  // [2 ranks][2 ks][96 rows][8] fp16, ks for kt = L
+long h4_pair_offset(int M) { return M == 16 ? kH4PairOffset : 0; }              // n_band 16 tables start with the fold / Hankel-16 parts
+bool use_h4(int B, long F, int M, const float* hist) {
+  return hist == nullptr && (long)B * (((long)F * M + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples) >= 96;
 }
-int h4_synthesis(const float* s, float* out, const float* tables, int B, long F, int off2, unsigned flags, cudaStream_t st) {
-  const bool trimmed = ((flags >> 8) & 0xF) == 2 && ((flags >> 12) & 0x1F) == 12;
-  pqmf::H4SynthesisParams p{};
-  p.s = s; p.out = out; p.F = F; p.o = off2 / 16; p.parity = 0; p.trim = (int)((flags >> 20) & 7u);
+bool h4_analysis_ok(const float* x, const float* y, long T, long F, int M) {
+  return T > 0 && (T % M) == 0 && (T % 4) == 0 && F == T / M && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
+}
+bool h4_synthesis_ok(const float* s, const float* out, long F) {
+  return F > 0 && (F & 3) == 0 && ((uintptr_t)s % 16) == 0 && ((uintptr_t)out % 32) == 0;
+}
+// taps kept by the images in `tables` (PQMF_FLAG_TAPS from pqmf_build_tables_f32); kt == 0: the caller did not pass them
+void h4_taps(unsigned flags, int& jlo, int& kt) {
+  jlo = 32 * (int)((flags >> 8) & 0xF);
+  kt = 32 * (int)((flags >> 12) & 0x1F);
+}
+
+template <int M>
+int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, unsigned flags, cudaStream_t st) {
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
-    p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset + kH4PairImageFloats);
-    const int e = trimmed ? pqmf::h4_launch_synthesis<64, 384, true>(p, B, st) : pqmf::h4_launch_synthesis<0, 512, true>(p, B, st);
+    p.g = pqmf::h4_shape(M, jlo, kt, true, false);
+    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M));
+    const int e = pqmf::h4_launch_analysis<M, true>(p, B, st);
+    if (e == 0) return 0;
+    (void)cudaGetLastError();  // a context that cannot co-schedule CTA pairs (e.g. an SM partition): same arithmetic, one CTA per SM
+  }
+  if constexpr (M != 16) {
+    return PQMF_ERR_UNSUPPORTED;  // single-CTA images are only built for n_band 16
+  } else {
+    p.g = pqmf::h4_shape(M, jlo, kt, false, false);
+    p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
+    return pqmf::h4_launch_analysis<M, false>(p, B, st);
+  }
+}
+int h4_analysis(const float* x, float* y, const float* tables, int B, long T, long F, int M, int L, unsigned flags, cudaStream_t st) {
+  int jlo, kt;
+  h4_taps(flags, jlo, kt);
+  if (kt == 0) return PQMF_ERR_UNSUPPORTED;
+  pqmf::H4AnalysisParams p{};
+  p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
+  switch (M) {
+    case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, flags, st);
+    case 16: return h4_analysis_m<16>(p, tables, jlo, kt, B, flags, st);
+    case 32: return h4_analysis_m<32>(p, tables, jlo, kt, B, flags, st);
+    default: return PQMF_ERR_UNSUPPORTED;
+  }
+}
+
+template <int M>
+int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
+  if (!(flags & PQMF_FLAG_NO_PAIR)) {
+    p.g = pqmf::h4_shape(M, jlo, kt, true, true);
+    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M) + h4_pair_floats(M, L));
+    const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st);
     if (e == 0) return 0;
     (void)cudaGetLastError();
   }
-  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
-  return trimmed ? pqmf::h4_launch_synthesis<64, 384>(p, B, st) : pqmf::h4_launch_synthesis<0, 512>(p, B, st);
+  if constexpr (M != 16) {
+    return PQMF_ERR_UNSUPPORTED;
+  } else {
+    p.g = pqmf::h4_shape(M, jlo, kt, false, true);
+    p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
+    return pqmf::h4_launch_synthesis<M, false>(p, B, st);
+  }
+}
+int h4_synthesis(const float* s, float* out, const float* tables, int B, long F, int off2, int M, int L, unsigned flags, cudaStream_t st) {
+  int jlo, kt;
+  h4_taps(flags, jlo, kt);
+  if (kt == 0 || off2 % M != 0) return PQMF_ERR_UNSUPPORTED;
+  pqmf::H4SynthesisParams p{};
+  p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0; p.trim = (int)((flags >> 20) & 7u);
+  switch (M) {
+    case 8: return h4_synthesis_m<8>(p, tables, jlo, kt, B, L, flags, st);
+    case 16: return h4_synthesis_m<16>(p, tables, jlo, kt, B, L, flags, st);
+    case 32: return h4_synthesis_m<32>(p, tables, jlo, kt, B, L, flags, st);
+    default: return PQMF_ERR_UNSUPPORTED;
+  }
 }
 
 // n_band 16 fast path: fold + tensor-core modulation (fast16*.cuh), or -- with PQMF_FLAG_EXACT -- the direct form as an
@@ -201,22 +253,30 @@ int exact_tc_synthesis(const float* s, const float* hist, float* out, float* his
 
 int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, const float* tables, int B, long T, long F, int off,
                   int parity, unsigned flags, cudaStream_t st) {
-  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, hist) && ((uintptr_t)y % 16) == 0)
-    return h4_analysis(x, y, tables, B, T, F, off, flags, st);
+  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, 16, hist) && h4_analysis_ok(x, y, T, F, 16) && off == 256) {
+    const int e = h4_analysis(x, y, tables, B, T, F, 16, 512, flags, st);
+    if (e != PQMF_ERR_UNSUPPORTED) return e;
+  }
   if (flags & PQMF_FLAG_EXACT) return exact_tc_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
   return pqmf::fast16_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
 }
 
 int fast_synthesis(const float* s, const float* hist, float* out, float* hist_out, const float* tables, int B, long F, int off2,
                    int parity, unsigned flags, cudaStream_t st) {
-  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, hist) && ((uintptr_t)out % 32) == 0 && ((uintptr_t)s % 16) == 0 && (F & 3) == 0 && off2 % 16 == 0)
-    return h4_synthesis(s, out, tables, B, F, off2, flags, st);
+  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, 16, hist) && h4_synthesis_ok(s, out, F)) {
+    const int e = h4_synthesis(s, out, tables, B, F, off2, 16, 512, flags, st);
+    if (e != PQMF_ERR_UNSUPPORTED) return e;
+  }
   if (flags & PQMF_FLAG_EXACT) return exact_tc_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
   return pqmf::fast16_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
 }
 
 bool use_fast(int M, int L, const float* tables, unsigned flags) {
   return tables != nullptr && !(flags & PQMF_FLAG_NO_SIGN) && pqmf::hankel16_supported(M, L);
+}
+// n_band 8 / 32: only the offline Hankel kernels exist (exact mode, streaming and the sign-less free functions use the direct form)
+bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
+  return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && h4_family(M, L);
 }
 
 }  // namespace
@@ -237,14 +297,46 @@ const char* pqmf_strerror(int code) {
 
 unsigned long long pqmf_launch_count(void) { return g_launches.load(); }
 
-int pqmf_path_for(int M, int L, const float* tables, unsigned flags) { return use_fast(M, L, tables, flags) ? 1 : 0; }
+int pqmf_path_for(int M, int L, const float* tables, unsigned flags) {
+  return (use_fast(M, L, tables, flags) || use_h4_family(M, L, tables, flags)) ? 1 : 0;
+}
 
-long pqmf_tables_numel(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4PairOffset + 2L * kH4PairImageFloats : 0; }
+long pqmf_tables_numel(int M, int L) {
+  if (pqmf::hankel16_supported(M, L)) return kH4PairOffset + 2L * kH4PairImageFloats;
+  return h4_family(M, L) ? 2L * h4_pair_floats(M, L) : 0;
+}
 
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
                           double* residual, unsigned* fast_flags) {
   if (!hk_host || !h_host || !tables_host || N <= 0 || N > L) return PQMF_ERR_ARG;
-  if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
+  if (!pqmf::hankel16_supported(M, L)) {
+    if (!h4_family(M, L)) return PQMF_ERR_UNSUPPORTED;
+    // ---- n_band 8 / 32: CTA-pair images of the offline Hankel kernels only.  Taps kept = the 32-aligned span of non-zero columns.
+    int first = L, last = -1;
+    for (int k = 0; k < M; ++k)
+      for (int j = 0; j < L; ++j)
+        if (hk_host[(size_t)k * L + j] != 0.f) {
+          first = j < first ? j : first;
+          last = j > last ? j : last;
+        }
+    if (last < 0) return PQMF_ERR_UNSUPPORTED;
+    const int jlo = (first / 32) * 32, kt = ((last + 32) / 32) * 32 - jlo;
+    if (jlo / 32 > 15 || kt / 32 > 31) return PQMF_ERR_UNSUPPORTED;
+    if (!pqmf::h4_shape_fits(pqmf::h4_shape(M, jlo, kt, true, false)) || !pqmf::h4_shape_fits(pqmf::h4_shape(M, jlo, kt, true, true)))
+      return PQMF_ERR_UNSUPPORTED;  // bank too long for one SM's shared memory: direct form
+    std::memset(tables_host, 0, (size_t)pqmf_tables_numel(M, L) * sizeof(float));
+    const int ks = (kt + 64 - M + 15) / 16;
+    std::vector<uint16_t> ia((size_t)2 * ks * 128 * 8), is((size_t)2 * ks * 128 * 8);
+    pqmf::hankel4_build_banks(hk_host, M, L, jlo, kt, ia.data(), is.data());
+    uint16_t* imgp = reinterpret_cast<uint16_t*>(tables_host);
+    pqmf::hankel4_pair_image(ia.data(), ks, imgp);
+    pqmf::hankel4_pair_image(is.data(), ks, imgp + 2 * h4_pair_floats(M, L));
+    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt, false, 4e-6);
+    const int trim_s = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt, true, 9e-6);
+    if (residual) *residual = 0.0;
+    if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s);
+    return PQMF_OK;
+  }
   std::memset(tables_host, 0, (size_t)pqmf_tables_numel(M, L) * sizeof(float));
   // ---- part 1: fold + modulation tables  [ g (L) | c1 (M*2M) | c2 (M*2M) ]
   // hk[k, r + 2M q] = (-1)^q * 2 hpad[r + 2M q] * cos((2k+1) pi/(2M) (r - c0) + (-1)^k pi/4)   
@@ -294,14 +386,15 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   pqmf::hankel16_build_banks(hk_host, jlo, kt, img, img + (size_t)kt * 32);
   // ---- part 3: the same bank replicated at four frame offsets for the offline default path (hankel4.cuh)
   uint16_t* img4 = reinterpret_cast<uint16_t*>(tables_host + kH4TableOffset);
-  pqmf::hankel4_build_banks(hk_host, jlo, kt, img4, img4 + 2 * kH4ImageFloats);
+  pqmf::hankel4_build_banks(hk_host, 16, 512, jlo, kt, img4, img4 + 2 * kH4ImageFloats);
+  const int ks4 = (kt + 64 - 16 + 15) / 16;
   uint16_t* imgp = reinterpret_cast<uint16_t*>(tables_host + kH4PairOffset);
-  pqmf::hankel4_pair_image(img4, kt, imgp);
-  pqmf::hankel4_pair_image(img4 + 2 * kH4ImageFloats, kt, imgp + 2 * kH4PairImageFloats);
+  pqmf::hankel4_pair_image(img4, ks4, imgp);
+  pqmf::hankel4_pair_image(img4 + 2 * kH4ImageFloats, ks4, imgp + 2 * kH4PairImageFloats);
   // edge K-steps of the Hankel-4 kernels that may skip the fp16 correction terms: worst-case added error, per unit of
   // max|input|, 4e-6 (analysis) / 9e-6 (synthesis, all 16 bands at full scale); typical random-signal error is ~50x lower
-  const int trim_a = pqmf::hankel4_pick_trim(hk_host, jlo, kt, false, 4e-6);
-  const int trim_s = pqmf::hankel4_pick_trim(hk_host, jlo, kt, true, 9e-6);
+  const int trim_a = pqmf::hankel4_pick_trim(hk_host, 16, 512, jlo, kt, false, 4e-6);
+  const int trim_s = pqmf::hankel4_pick_trim(hk_host, 16, 512, jlo, kt, true, 9e-6);
   if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s);
   return PQMF_OK;
 }
@@ -316,6 +409,10 @@ int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* ta
     int e = fast_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
+  if (M != 16 && use_h4_family(M, L, tables, flags) && h4_analysis_ok(x, y, T, n_frames, M) && use_h4(B, n_frames, M, nullptr)) {
+    int e = h4_analysis(x, y, tables, B, T, n_frames, M, L, flags, st);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
   return analysis_direct(x, nullptr, y, hk, B, T, n_frames, M, L, L / 2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
 }
 
@@ -328,6 +425,10 @@ int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float*
   const int off2 = L / 2 - delay_frames * M;
   if (use_fast(M, L, tables, flags) && pqmf::hankel16_synthesis_ok(s, out, n_frames)) {
     int e = fast_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, flags, st);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  if (M != 16 && use_h4_family(M, L, tables, flags) && h4_synthesis_ok(s, out, n_frames) && use_h4(B, n_frames, M, nullptr)) {
+    int e = h4_synthesis(s, out, tables, B, n_frames, off2, M, L, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
   return synthesis_direct(s, nullptr, out, hk, B, n_frames, M, L, off2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);

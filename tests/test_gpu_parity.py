@@ -332,3 +332,27 @@ def test_hankel4_full_length_bank(golden, pq):
     s = y64.astype(np.float32)
     out = mod.inverse(dev(s)).cpu().numpy()
     assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
+
+
+# ------------------------------------------------------------------ n_band 8 / 32 on the 64-samples-per-row Hankel kernels
+@pytest.mark.parametrize("m,b,frames", ((8, 24, 4096), (8, 50, 2100), (32, 24, 1024), (32, 49, 516), (8, 3, 8192 * 5 + 4)))
+def test_hankel_other_band_counts_vs_oracle(golden, pq, m, b, frames):
+    """>= 96 tiles of 8192 samples: the dispatcher picks hankel4.cuh for n_band 8 and 32 too (same MMA shapes, N = 128)."""
+    hk = golden(f"bank_M{m}.npz")["hk"]
+    t = m * frames
+    x = O.audio_like((b, 1, t), 7 * m + frames)
+    mod = pq.PQMF(100, m).cuda()
+    assert mod._tables.numel() > 0
+    y = mod(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0], hk)
+    assert np.abs(y - y64).max() <= TOL / 2
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
+    # identical to the register-tiled direct form (exact=True) within the tolerance
+    ex = pq.PQMF(100, m, exact=True).cuda()
+    assert (ex(dev(x)).cpu().numpy() - y).__abs__().max() <= 3e-6
+    # CachedPQMF: one frame later
+    cached = pq.CachedPQMF(100, m).cuda()
+    oc = cached.inverse(dev(s)).cpu().numpy()
+    assert np.abs(oc[:, 0] - O.synthesis(s, hk, delay_frames=1)).max() <= TOL / 2
