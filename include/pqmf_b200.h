@@ -55,8 +55,8 @@ int pqmf_abi_version(void);
 const char* pqmf_strerror(int code);
 
 /* Which kernel family a call with these parameters would use: 0 = register-tiled direct form (generic),
- * 1 = the n_band 16 / L 512 tensor-core kernels (Hankel-4 offline, fold + modulation for streaming blocks and small
- * batches, Hankel-16 with PQMF_FLAG_EXACT).  `tables` may be NULL. */
+ * 1 = the tensor-core kernels: n_band 16 / L 512 (Hankel-4 offline, fold + modulation for streaming blocks and small
+ * batches, Hankel-16 with PQMF_FLAG_EXACT) and n_band 8 / 32 (Hankel offline, large batches).  `tables` may be NULL. */
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
 
 /* ---- coefficient tables for the fast path (host side, one-off; replaces nothing in the reference:
@@ -66,9 +66,10 @@ int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
  * tables_host must hold pqmf_tables_numel(M, L) floats: [ g (L) | C_hi (M*2M) | C_lo (M*2M) ] followed by the fp16 images of
  * hk in the tensor cores' shared-memory operand layout (Hankel-16 and Hankel-4 kernels, analysis and synthesis).
  * *fast_flags (may be NULL) receives the PQMF_FLAG_TAPS(...) bits describing which taps are pure zero padding and the
- * PQMF_FLAG_H4_TRIM(...) bits; OR them into the `flags` of the compute calls that are given these tables (optional:
- * without them the kernels run all L/2M taps and every correction term).
- * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path. */
+ * PQMF_FLAG_H4_TRIM(...) bits; OR them into the `flags` of every compute call that is given these tables (the images are
+ * built for exactly those taps: without the TAPS bits the offline Hankel kernels are not used).
+ * Supported: n_band 16 / L 512 (all kernel families) and n_band 8 / L 256, n_band 32 / L 1024 (offline Hankel kernels).
+ * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path or the bank does not fit one SM. */
 long pqmf_tables_numel(int M, int L);
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
                           double* residual, unsigned* fast_flags);
