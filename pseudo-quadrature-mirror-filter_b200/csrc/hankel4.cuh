@@ -256,10 +256,10 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim);
   } else {
     const int n_quads = g.rows * 16;
-    // this thread's share of the fp32 window of a tile, prefetched TWO tiles ahead straight from global memory into two register
-    // sets (with one tile of prefetch the DRAM latency of the loads was exposed every iteration once the tensor pipe was no
-    // longer the bottleneck: n_band 8 needs 16 K-steps per tile and ran no faster than n_band 16 with 27)
-    float4 x0[NQ], x1[NQ];
+    // this thread's share of the fp32 window of a tile, prefetched one tile ahead straight from global memory.  (Two tiles ahead
+    // in two register sets was measured on the same box: 6 % slower in bursts and sustained -- the extra live registers cost more
+    // than the latency they hide.)
+    float4 x0[NQ];
     auto load_window = [&](float4 (&xr)[NQ], unsigned bb, unsigned cc) {
       const long s0 = (long)cc * kH4TileSamples + g.jlo - p.off;
       const float* xrow = p.x + (size_t)bb * p.T;
@@ -347,22 +347,15 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
 
     unsigned b1 = b, c1 = c;  // tile it + 1
     advance(b1, c1);
-    unsigned b2 = b1, c2 = c1;  // tile it + 2
-    advance(b2, c2);
     load_window(x0, b, c);
-    if (n_iter > 1) load_window(x1, b1, c1);
     unsigned prev_b = 0, prev_c = 0;
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       H4_STAMP(0);
-      if (it & 1) convert(x1, pb);
-      else convert(x0, pb);
+      convert(x0, pb);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
-      if (it + 2 < n_iter) {  // refill the register set that was just consumed
-        if (it & 1) load_window(x1, b2, c2);
-        else load_window(x0, b2, c2);
-      }
+      if (it + 1 < n_iter) load_window(x0, b1, c1);  // consumed at the top of the next iteration
       H4_STAMP(2);
       H4_STAMP(3);
       if (it > 0) {
@@ -376,9 +369,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       prev_c = c;
       b = b1;
       c = c1;
-      b1 = b2;
-      c1 = c2;
-      advance(b2, c2);
+      advance(b1, c1);
     }
     ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
     ptx::tc_fence_after();
@@ -449,7 +440,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     const int n_fq = g.rows * FR / 4;                        // frame quads per plane
     const int bg = tid / n_fq, fq = tid - bg * n_fq;
     const bool has_item = tid < n_fq * NBG;
-    float4 v0[8], v1[8];  // two register sets: loads run two tiles ahead (see the analysis kernel)
+    float4 v0[8];  // prefetched one tile ahead
     auto load_frames = [&](float4 (&v)[8], unsigned bb, unsigned cc) {
       const long n = (long)cc * (kH4Rows * FR) + nbase + 4 * fq;
       const float* sp = p.s + ((size_t)bb * M + 8 * bg) * p.F + n;
@@ -535,22 +526,15 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
 
     unsigned b1 = b, c1 = c;
     advance(b1, c1);
-    unsigned b2 = b1, c2 = c1;
-    advance(b2, c2);
     load_frames(v0, b, c);
-    if (n_iter > 1) load_frames(v1, b1, c1);
     unsigned prev_b = 0, prev_c = 0;
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       H4_STAMP(0);
-      if (it & 1) convert(v1, pb);
-      else convert(v0, pb);
+      convert(v0, pb);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
-      if (it + 2 < n_iter) {
-        if (it & 1) load_frames(v1, b2, c2);
-        else load_frames(v0, b2, c2);
-      }
+      if (it + 1 < n_iter) load_frames(v0, b1, c1);
       H4_STAMP(2);
       H4_STAMP(3);
       if (it > 0) {
@@ -565,9 +549,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       prev_c = c;
       b = b1;
       c = c1;
-      b1 = b2;
-      c1 = c2;
-      advance(b2, c2);
+      advance(b1, c1);
     }
     ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
     ptx::tc_fence_after();
