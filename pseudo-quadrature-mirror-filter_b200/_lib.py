@@ -18,6 +18,7 @@ _CABI_PATH = os.path.join(_HERE, "libpqmf_b200.so")
 _TORCH_PATH = os.path.join(_HERE, "libpqmf_b200_torch.so")
 _BUILD_HINT = "build it with:  python -c 'import __graft_entry__ as g; g.build()'   (or make -C {}/csrc all torch)".format(_HERE)
 
+PQMF_ERR_UNSUPPORTED = -2
 PQMF_FLAG_EXACT = 1
 PQMF_FLAG_NO_SIGN = 2
 PQMF_FLAG_FOLD = 4
@@ -105,6 +106,9 @@ def build_tables(hk: torch.Tensor, h: torch.Tensor):
     out = torch.empty(n, dtype=torch.float32)
     res = ctypes.c_double(0.0)
     fast_flags = ctypes.c_uint(0)
-    check(cabi.pqmf_build_tables_f32(hk_c.data_ptr(), h_c.data_ptr(), int(h_c.numel()), m, length, out.data_ptr(),
-                                     ctypes.byref(res), ctypes.byref(fast_flags)), "pqmf_build_tables_f32")
+    rc = cabi.pqmf_build_tables_f32(hk_c.data_ptr(), h_c.data_ptr(), int(h_c.numel()), m, length, out.data_ptr(),
+                                    ctypes.byref(res), ctypes.byref(fast_flags))
+    if rc == PQMF_ERR_UNSUPPORTED:  # e.g. a bank too long for one SM's shared memory (n_band 32 at attenuation 120): direct form
+        return torch.zeros(0, dtype=torch.float32), float("nan"), 0
+    check(rc, "pqmf_build_tables_f32")
     return out, float(res.value), int(fast_flags.value)

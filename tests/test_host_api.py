@@ -157,3 +157,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_tables_exist_for_the_tensor_core_band_counts_and_degrade_gracefully():
+    """n_band 8 / 16 / 32 get tensor-core tables (with the tap span and trim facts in the flags); banks the kernels cannot hold
+    (n_band 32 at attenuation 120: 1024 taps) and other band counts fall back to the direct form instead of raising."""
+    import pqmf_b200 as pq
+
+    for m, jlo, kt in ((8, 32, 192), (16, 64, 384), (32, 128, 768)):
+        mod = pq.PQMF(100, m)
+        assert mod._tables.numel() > 0
+        assert 32 * ((mod._flags >> 8) & 15) == jlo and 32 * ((mod._flags >> 12) & 31) == kt
+        assert 0 < ((mod._flags >> 17) & 7) <= 7 and 0 < ((mod._flags >> 20) & 7) <= 7
+    for att, m in ((120, 32), (100, 4), (100, 64), (100, 2)):
+        mod = pq.PQMF(att, m)
+        assert mod._tables.numel() == 0 and (mod._flags >> 8) == 0
