@@ -142,9 +142,10 @@ constexpr long kH4PairOffset = kH4TableOffset + 2 * kH4ImageFloats;
 constexpr long kH4PairImageFloats = 2L * 35 * 3072 / 4;  // per-rank images of the CTA-pair kernels (fp16 [2][2 KS][96][8])
 
 // ---- offline default for n_band 8 / 16 / 32: the 64-samples-per-row Hankel GEMM (hankel4.cuh) when there are enough tiles ----
-bool h4_family(int M, int L) { return (M == 8 || M == 16 || M == 32) && L == 32 * M; }
+// prototype lengths: L = 32 M at attenuation ~100, 16 M / 64 M for shorter / longer designs
+bool h4_family(int M, int L) { return (M == 8 || M == 16 || M == 32) && (L == 16 * M || L == 32 * M || L == 64 * M); }
 long h4_pair_floats(int M, int L) { return 1536L * ((L + 64 - M + 15) / 16); }  // [2 ranks][2 ks][96 rows][8] fp16, ks for kt = L
-long h4_pair_offset(int M) { return M == 16 ? kH4PairOffset : 0; }              // n_band 16 tables start with the fold / Hankel-16 parts
+long h4_pair_offset(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4PairOffset : 0; }  // those tables start with the fold / Hankel-16 parts
 bool use_h4(int B, long F, int M, const float* hist) {
   return hist == nullptr && (long)B * (((long)F * M + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples) >= 96;
 }
@@ -161,16 +162,16 @@ void h4_taps(unsigned flags, int& jlo, int& kt) {
 }
 
 template <int M>
-int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, unsigned flags, cudaStream_t st) {
+int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
     p.g = pqmf::h4_shape(M, jlo, kt, true, false);
-    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M));
+    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L));
     const int e = pqmf::h4_launch_analysis<M, true>(p, B, st);
     if (e == 0) return 0;
     (void)cudaGetLastError();  // a context that cannot co-schedule CTA pairs (e.g. an SM partition): same arithmetic, one CTA per SM
   }
-  if constexpr (M != 16) {
-    return PQMF_ERR_UNSUPPORTED;  // single-CTA images are only built for n_band 16
+  if (!pqmf::hankel16_supported(M, L)) {
+    return PQMF_ERR_UNSUPPORTED;  // single-CTA images are only built for n_band 16 / L 512
   } else {
     p.g = pqmf::h4_shape(M, jlo, kt, false, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
@@ -184,9 +185,9 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   pqmf::H4AnalysisParams p{};
   p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
   switch (M) {
-    case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, flags, st);
-    case 16: return h4_analysis_m<16>(p, tables, jlo, kt, B, flags, st);
-    case 32: return h4_analysis_m<32>(p, tables, jlo, kt, B, flags, st);
+    case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, L, flags, st);
+    case 16: return h4_analysis_m<16>(p, tables, jlo, kt, B, L, flags, st);
+    case 32: return h4_analysis_m<32>(p, tables, jlo, kt, B, L, flags, st);
     default: return PQMF_ERR_UNSUPPORTED;
   }
 }
@@ -195,12 +196,12 @@ template <int M>
 int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
     p.g = pqmf::h4_shape(M, jlo, kt, true, true);
-    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M) + h4_pair_floats(M, L));
+    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + h4_pair_floats(M, L));
     const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st);
     if (e == 0) return 0;
     (void)cudaGetLastError();
   }
-  if constexpr (M != 16) {
+  if (!pqmf::hankel16_supported(M, L)) {
     return PQMF_ERR_UNSUPPORTED;
   } else {
     p.g = pqmf::h4_shape(M, jlo, kt, false, true);
@@ -409,7 +410,7 @@ int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* ta
     int e = fast_analysis(x, nullptr, y, nullptr, tables, B, T, n_frames, L / 2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
-  if (M != 16 && use_h4_family(M, L, tables, flags) && h4_analysis_ok(x, y, T, n_frames, M) && use_h4(B, n_frames, M, nullptr)) {
+  if (!pqmf::hankel16_supported(M, L) && use_h4_family(M, L, tables, flags) && h4_analysis_ok(x, y, T, n_frames, M) && use_h4(B, n_frames, M, nullptr)) {
     int e = h4_analysis(x, y, tables, B, T, n_frames, M, L, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
@@ -427,7 +428,7 @@ int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float*
     int e = fast_synthesis(s, nullptr, out, nullptr, tables, B, n_frames, off2, 0, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
-  if (M != 16 && use_h4_family(M, L, tables, flags) && h4_synthesis_ok(s, out, n_frames) && use_h4(B, n_frames, M, nullptr)) {
+  if (!pqmf::hankel16_supported(M, L) && use_h4_family(M, L, tables, flags) && h4_synthesis_ok(s, out, n_frames) && use_h4(B, n_frames, M, nullptr)) {
     int e = h4_synthesis(s, out, tables, B, n_frames, off2, M, L, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
