@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     // ---- workers.  Item (fq, bg): frames 4 fq .. 4 fq + 3 of bands 8 bg .. 8 bg + 7 = eight float4 loads (prefetched one
     //      tile ahead) -> four 16-byte chunks per fp16 plane.  bg-major thread order keeps a quarter-warp on eight consecutive
     //      frame quads of one band group: their SWIZZLE_128B images hit eight different bank groups at n_band 8 and 16.
-    const int n_fq = g.rows * FR / 4;                        // frame quads per plane
+    const int n_fq = (g.rows * FR + 3) / 4;                  // frame quads per plane (the last one may run into the plane's padding)
     const int bg = tid / n_fq, fq = tid - bg * n_fq;
     const bool has_item = tid < n_fq * NBG;
     float4 v0[8];  // prefetched one tile ahead
