@@ -48,6 +48,9 @@ extern "C" {
 /* from pqmf_build_tables_f32: edge K-steps (analysis, synthesis) of the offline n_band 16 kernels whose fp16 correction
  * terms are provably below 4e-6 / 9e-6 of max|input| for this bank and are skipped; 0 keeps every term */
 #define PQMF_FLAG_H4_TRIM(ta, ts) (((unsigned)(ta) << 17) | ((unsigned)(ts) << 20))
+/* from pqmf_build_tables_f32: the bank is too long for one SM's shared memory; the tables hold two tap ranges (TAPS = one of
+ * them) that run as two launches, the second accumulating into the output (n_band 64, long prototypes at n_band 32) */
+#define PQMF_FLAG_H4_SPLIT (1u << 23)
 
 typedef void* pqmf_stream_t; /* cudaStream_t */
 
@@ -68,7 +71,7 @@ int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
  * *fast_flags (may be NULL) receives the PQMF_FLAG_TAPS(...) bits describing which taps are pure zero padding and the
  * PQMF_FLAG_H4_TRIM(...) bits; OR them into the `flags` of every compute call that is given these tables (the images are
  * built for exactly those taps: without the TAPS bits the offline Hankel kernels are not used).
- * Supported: n_band 16 / L 512 (all kernel families); n_band 8 / 16 / 32 with L = 16, 32 or 64 n_band (offline Hankel kernels).
+ * Supported: n_band 16 / L 512 (all kernel families); n_band 8 / 16 / 32 / 64 with L = 16, 32 or 64 n_band (offline Hankel kernels).
  * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path or the bank does not fit one SM. */
 long pqmf_tables_numel(int M, int L);
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,

@@ -71,13 +71,13 @@ inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
 }
 inline bool h4_shape_fits(const H4Shape& g) { return g.rows <= kH4MaxPlaneRows && g.bytes <= 227 * 1024; }
 
-// one elected lane: the MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T.  The first and last `trim`
+// one elected lane: the MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T.  The first `tlo` and last `thi`
 // K-steps carry only the tails of the prototype: there the two correction terms (h1 c2, h2 c1) are below the error budget
 // that pqmf_build_tables_f32 checked against the actual bank, so those steps run h1 c1 alone (N = 64) and no h2 pass.
 // `pad_bytes` shifts the A windows (synthesis alignment).
 template <bool PAIR>
 __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int ks,
-                                              int pad_bytes, int trim) {
+                                              int pad_bytes, int tlo, int thi) {
   constexpr uint32_t kBankRows = PAIR ? 96 : 128;
   const uint64_t da1 = umma_desc_sw128(plane1_addr), da2 = umma_desc_sw128(plane2_addr);
   const uint64_t db = ptx::umma_desc(bank_addr, kBankRows * 16, 128);                          // N = 128 operand: bank rows from 0
@@ -93,20 +93,19 @@ __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_a
     if constexpr (PAIR) ptx::umma_pair_f16(d_tmem, a, bdesc, idesc, acc);
     else ptx::umma_f16(d_tmem, a, bdesc, idesc, acc);
   };
-  for (int s = trim; s < ks - trim; ++s) mma(da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != trim);
-  for (int s = 0; s < trim; ++s) {
-    mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
-    mma(da1 + a_step(ks - 1 - s), db64 + (uint64_t)(kStep * (ks - 1 - s)), idesc64, true);
-  }
-  for (int s = trim; s < ks - trim; ++s) mma(da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = tlo; s < ks - thi; ++s) mma(da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != tlo);  // initialises all 128 columns
+  for (int s = 0; s < tlo; ++s) mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = ks - thi; s < ks; ++s) mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = tlo; s < ks - thi; ++s) mma(da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
 }
 
 template <int N>
 __device__ __forceinline__ void h4_tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
-  static_assert(N == 4 || N == 8 || N == 16, "columns per load");
+  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "columns per load");
   if constexpr (N == 4) ptx::tmem_ld4(taddr, r);
   else if constexpr (N == 8) ptx::tmem_ld8(taddr, r);
-  else ptx::tmem_ld16(taddr, r);
+  else if constexpr (N == 16) ptx::tmem_ld16(taddr, r);
+  else ptx::tmem_ld32(taddr, r);
 }
 
 #ifdef PQMF_H4_TRACE
@@ -180,7 +179,8 @@ __device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp) {
 // the issuer warp's loop (leader CTA only): tcgen05.mma issue blocks once the tensor pipe's queue is full (a 54-MMA group keeps
 // the issuing thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
 template <bool PAIR>
-__device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g, uint32_t tmem, unsigned n_iter, int pad_bytes, int trim) {
+__device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g, uint32_t tmem, unsigned n_iter, int pad_bytes, int tlo,
+                                               int thi) {
   const uint32_t bank_addr = ptx::smem_u32(s.bank), plane_addr = ptx::smem_u32(s.planes);
   for (unsigned it = 0; it < n_iter; ++it) {
     const int pb = (int)(it & 1);
@@ -188,7 +188,7 @@ __device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g
     ptx::tc_fence_after();
     if (ptx::elect_one_sync()) {
       h4_issue_mmas<PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * g.plane, plane_addr + (2 * pb + 1) * g.plane, bank_addr, g.ks,
-                          pad_bytes, trim);
+                          pad_bytes, tlo, thi);
       if constexpr (PAIR) ptx::umma_pair_commit(&s.mma_bar[pb]);
       else ptx::umma_commit(&s.mma_bar[pb]);
     }
@@ -219,7 +219,8 @@ struct H4AnalysisParams {
   long T, F;
   int off;               // L / 2 (offline only: streaming blocks are far smaller than a tile)
   int parity;
-  int trim;              // edge K-steps without correction terms (h4_issue_mmas)
+  int trim_lo, trim_hi;  // edge K-steps without correction terms (h4_issue_mmas)
+  int accumulate;        // add to what y already holds (second launch of a bank split in two tap ranges)
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
 #endif
 
   if (warp == kMmaWarp) {
-    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim);
+    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim_lo, p.trim_hi);
   } else {
     const int n_quads = g.rows * 16;
     // this thread's share of the fp32 window of a tile, prefetched one tile ahead straight from global memory.  (Two tiles ahead
@@ -324,6 +325,17 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       }
       float* yp = p.y + ((size_t)bb * M + HB * hb) * p.F + n;
       if (n + FR - 1 < p.F && (p.F % (FR >= 4 ? 4 : FR)) == 0) {
+        if (p.accumulate) {  // second tap range of a split bank: all the reads first, so they overlap instead of alternating with the stores
+          float prev[FR][HB];
+#pragma unroll
+          for (int kk = 0; kk < HB; ++kk)
+#pragma unroll
+            for (int dl = 0; dl < FR; ++dl) prev[dl][kk] = __ldcs(yp + (size_t)kk * p.F + dl);
+#pragma unroll
+          for (int kk = 0; kk < HB; ++kk)
+#pragma unroll
+            for (int dl = 0; dl < FR; ++dl) v[dl][kk] += prev[dl][kk];
+        }
 #pragma unroll
         for (int kk = 0; kk < HB; ++kk) {
           float* q = yp + (size_t)kk * p.F;
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
         for (int kk = 0; kk < HB; ++kk)
 #pragma unroll
           for (int dl = 0; dl < FR; ++dl)
-            if (n + dl < p.F) yp[(size_t)kk * p.F + dl] = v[dl][kk];
+            if (n + dl < p.F) yp[(size_t)kk * p.F + dl] = v[dl][kk] + (p.accumulate ? yp[(size_t)kk * p.F + dl] : 0.f);
       }
     };
 
@@ -397,7 +409,8 @@ struct H4SynthesisParams {
   long F;
   int o;                 // off2 / M: L / (2 M) (PQMF.inverse) or one less (CachedPQMF.inverse)
   int parity;
-  int trim;
+  int trim_lo, trim_hi;
+  int accumulate;        // add to what out already holds
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
   const int pad = (p.o - ehi) & 3;
   const int nbase = p.o - ehi - pad;  // multiple of 4 (may be negative)
   if (warp == kMmaWarp) {
-    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 2 * M * pad, p.trim);
+    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 2 * M * pad, p.trim_lo, p.trim_hi);
   } else {
     // ---- workers.  Item (fq, bg): frames 4 fq .. 4 fq + 3 of bands 8 bg .. 8 bg + 7 = eight float4 loads (prefetched one
     //      tile ahead) -> four 16-byte chunks per fp16 plane.  bg-major thread order keeps a quarter-warp on eight consecutive
@@ -521,7 +534,15 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       float* op = p.out + (size_t)bb * total + t0;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (t0 + 64 * q + 7 < total) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
+        if (t0 + 64 * q + 7 < total) {
+          if (p.accumulate) {
+            float prev[8];
+            ptx::ldg256_cs(op + (size_t)q * 64, prev);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) val[q][e] += prev[e];
+          }
+          ptx::stg256_cs(op + (size_t)q * 64, val[q]);
+        }
     };
 
     unsigned b1 = b, c1 = c;

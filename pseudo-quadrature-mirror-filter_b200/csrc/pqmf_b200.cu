@@ -141,11 +141,20 @@ constexpr long kH4ImageFloats = 35L * 4096 / 4;        // one hankel4 bank image
 constexpr long kH4PairOffset = kH4TableOffset + 2 * kH4ImageFloats;
 constexpr long kH4PairImageFloats = 2L * 35 * 3072 / 4;  // per-rank images of the CTA-pair kernels (fp16 [2][2 KS][96][8])
 
-// ---- offline default for n_band 8 / 16 / 32: the 64-samples-per-row Hankel GEMM (hankel4.cuh) when there are enough tiles ----
+// ---- offline default for n_band 8 / 16 / 32 / 64: the 64-samples-per-row Hankel GEMM (hankel4.cuh) when there are enough tiles ----
 // prototype lengths: L = 32 M at attenuation ~100, 16 M / 64 M for shorter / longer designs
-bool h4_family(int M, int L) { return (M == 8 || M == 16 || M == 32) && (L == 16 * M || L == 32 * M || L == 64 * M); }
-long h4_pair_floats(int M, int L) { return 1536L * ((L + 64 - M + 15) / 16); }  // [2 ranks][2 ks][96 rows][8] fp16, ks for kt = L
+bool h4_family(int M, int L) { return (M == 8 || M == 16 || M == 32 || M == 64) && (L == 16 * M || L == 32 * M || L == 64 * M); }
+int h4_ks(int M, int kt) { return (kt + 64 - M + 15) / 16; }
+// one CTA-pair image = [2 ranks][2 ks][96 rows][8] fp16 = 1536 ks floats.  Region sizes are fixed by (M, L) alone: a bank that
+// fits one SM uses [analysis | synthesis], sized for kt = L; a longer one is SPLIT into two tap ranges that run as two launches
+// (the second accumulates): [analysis lo | analysis hi | synthesis lo | synthesis hi], each sized for kt = L / 2.
+long h4_pair_floats(int M, int L) { return 1536L * h4_ks(M, L); }
+long h4_half_floats(int M, int L) { return 1536L * h4_ks(M, L / 2); }
 long h4_pair_offset(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4PairOffset : 0; }  // those tables start with the fold / Hankel-16 parts
+long h4_tables_floats(int M, int L) {
+  const long whole = 2 * h4_pair_floats(M, L), split = 4 * h4_half_floats(M, L);
+  return whole > split ? whole : split;
+}
 bool use_h4(int B, long F, int M, const float* hist) {
   return hist == nullptr && (long)B * (((long)F * M + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples) >= 96;
 }
@@ -155,7 +164,8 @@ bool h4_analysis_ok(const float* x, const float* y, long T, long F, int M) {
 bool h4_synthesis_ok(const float* s, const float* out, long F) {
   return F > 0 && (F & 3) == 0 && ((uintptr_t)s % 16) == 0 && ((uintptr_t)out % 32) == 0;
 }
-// taps kept by the images in `tables` (PQMF_FLAG_TAPS from pqmf_build_tables_f32); kt == 0: the caller did not pass them
+// taps kept by the images in `tables` (PQMF_FLAG_TAPS from pqmf_build_tables_f32); kt == 0: the caller did not pass them.
+// With PQMF_FLAG_H4_SPLIT the field holds half the span.
 void h4_taps(unsigned flags, int& jlo, int& kt) {
   jlo = 32 * (int)((flags >> 8) & 0xF);
   kt = 32 * (int)((flags >> 12) & 0x1F);
@@ -163,6 +173,19 @@ void h4_taps(unsigned flags, int& jlo, int& kt) {
 
 template <int M>
 int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
+  const int trim = (int)((flags >> 17) & 7u);
+  if (flags & PQMF_FLAG_H4_SPLIT) {  // two tap ranges, two launches; only the outer edge of each range may skip the corrections
+    for (int half = 0; half < 2; ++half) {
+      p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, false);
+      p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + half * h4_half_floats(M, L));
+      p.trim_lo = half ? 0 : trim;
+      p.trim_hi = half ? trim : 0;
+      p.accumulate = half;
+      if (const int e = pqmf::h4_launch_analysis<M, true>(p, B, st)) return half ? e : PQMF_ERR_UNSUPPORTED;
+    }
+    return 0;
+  }
+  p.trim_lo = p.trim_hi = trim;
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
     p.g = pqmf::h4_shape(M, jlo, kt, true, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L));
@@ -170,9 +193,10 @@ int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt
     if (e == 0) return 0;
     (void)cudaGetLastError();  // a context that cannot co-schedule CTA pairs (e.g. an SM partition): same arithmetic, one CTA per SM
   }
-  if (!pqmf::hankel16_supported(M, L)) {
+  if constexpr (M != 16) {
     return PQMF_ERR_UNSUPPORTED;  // single-CTA images are only built for n_band 16 / L 512
   } else {
+    if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
     p.g = pqmf::h4_shape(M, jlo, kt, false, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
     return pqmf::h4_launch_analysis<M, false>(p, B, st);
@@ -183,17 +207,32 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   h4_taps(flags, jlo, kt);
   if (kt == 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4AnalysisParams p{};
-  p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.trim = (int)((flags >> 17) & 7u);
+  p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0;
   switch (M) {
     case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, L, flags, st);
     case 16: return h4_analysis_m<16>(p, tables, jlo, kt, B, L, flags, st);
     case 32: return h4_analysis_m<32>(p, tables, jlo, kt, B, L, flags, st);
+    case 64: return h4_analysis_m<64>(p, tables, jlo, kt, B, L, flags, st);
     default: return PQMF_ERR_UNSUPPORTED;
   }
 }
 
 template <int M>
 int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
+  const int trim = (int)((flags >> 20) & 7u);
+  if (flags & PQMF_FLAG_H4_SPLIT) {
+    for (int half = 0; half < 2; ++half) {
+      p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, true);
+      p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + (2 + half) * h4_half_floats(M, L));
+      // synthesis K-steps run from the largest lag (the END of the tap range) down: the outer edge of the low range is its last steps
+      p.trim_lo = half ? trim : 0;
+      p.trim_hi = half ? 0 : trim;
+      p.accumulate = half;
+      if (const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st)) return half ? e : PQMF_ERR_UNSUPPORTED;
+    }
+    return 0;
+  }
+  p.trim_lo = p.trim_hi = trim;
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
     p.g = pqmf::h4_shape(M, jlo, kt, true, true);
     p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + h4_pair_floats(M, L));
@@ -201,9 +240,10 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
     if (e == 0) return 0;
     (void)cudaGetLastError();
   }
-  if (!pqmf::hankel16_supported(M, L)) {
+  if constexpr (M != 16) {
     return PQMF_ERR_UNSUPPORTED;
   } else {
+    if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
     p.g = pqmf::h4_shape(M, jlo, kt, false, true);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
     return pqmf::h4_launch_synthesis<M, false>(p, B, st);
@@ -214,11 +254,12 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
   h4_taps(flags, jlo, kt);
   if (kt == 0 || off2 % M != 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisParams p{};
-  p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0; p.trim = (int)((flags >> 20) & 7u);
+  p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0;
   switch (M) {
     case 8: return h4_synthesis_m<8>(p, tables, jlo, kt, B, L, flags, st);
     case 16: return h4_synthesis_m<16>(p, tables, jlo, kt, B, L, flags, st);
     case 32: return h4_synthesis_m<32>(p, tables, jlo, kt, B, L, flags, st);
+    case 64: return h4_synthesis_m<64>(p, tables, jlo, kt, B, L, flags, st);
     default: return PQMF_ERR_UNSUPPORTED;
   }
 }
@@ -304,7 +345,7 @@ int pqmf_path_for(int M, int L, const float* tables, unsigned flags) {
 
 long pqmf_tables_numel(int M, int L) {
   if (pqmf::hankel16_supported(M, L)) return kH4PairOffset + 2L * kH4PairImageFloats;
-  return h4_family(M, L) ? 2L * h4_pair_floats(M, L) : 0;
+  return h4_family(M, L) ? h4_tables_floats(M, L) : 0;
 }
 
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,
@@ -312,7 +353,8 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   if (!hk_host || !h_host || !tables_host || N <= 0 || N > L) return PQMF_ERR_ARG;
   if (!pqmf::hankel16_supported(M, L)) {
     if (!h4_family(M, L)) return PQMF_ERR_UNSUPPORTED;
-    // ---- n_band 8 / 32: CTA-pair images of the offline Hankel kernels only.  Taps kept = the 32-aligned span of non-zero columns.
+    // ---- other band counts / prototype lengths: CTA-pair images of the offline Hankel kernels only.  Taps kept = the span of
+    //      non-zero columns rounded to the alignment the kernels need (32 for the flag fields, n_band for whole synthesis lags).
     int first = L, last = -1;
     for (int k = 0; k < M; ++k)
       for (int j = 0; j < L; ++j)
@@ -321,21 +363,43 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
           last = j > last ? j : last;
         }
     if (last < 0) return PQMF_ERR_UNSUPPORTED;
-    const int jlo = (first / 32) * 32, kt = ((last + 32) / 32) * 32 - jlo;
+    const int al = M > 32 ? M : 32;
+    int jlo = (first / al) * al, kt = ((last + al) / al) * al - jlo;
+    auto fits = [&](int j0, int k0) {
+      return pqmf::h4_shape_fits(pqmf::h4_shape(M, j0, k0, true, false)) && pqmf::h4_shape_fits(pqmf::h4_shape(M, j0, k0, true, true));
+    };
+    bool split = false;
+    if (!fits(jlo, kt)) {  // too long for one SM's shared memory: two tap ranges of equal length, two launches
+      if (kt % (2 * al) != 0) {
+        if (jlo + kt + al <= L) kt += al;
+        else if (jlo >= al) { jlo -= al; kt += al; }
+        else return PQMF_ERR_UNSUPPORTED;
+      }
+      kt /= 2;
+      split = true;
+      if (!fits(jlo, kt) || !fits(jlo + kt, kt) || h4_ks(M, kt) > h4_ks(M, L / 2)) return PQMF_ERR_UNSUPPORTED;
+    }
     if (jlo / 32 > 15 || kt / 32 > 31) return PQMF_ERR_UNSUPPORTED;
-    if (!pqmf::h4_shape_fits(pqmf::h4_shape(M, jlo, kt, true, false)) || !pqmf::h4_shape_fits(pqmf::h4_shape(M, jlo, kt, true, true)))
-      return PQMF_ERR_UNSUPPORTED;  // bank too long for one SM's shared memory: direct form
     std::memset(tables_host, 0, (size_t)pqmf_tables_numel(M, L) * sizeof(float));
-    const int ks = (kt + 64 - M + 15) / 16;
+    uint16_t* base = reinterpret_cast<uint16_t*>(tables_host);
+    const int ks = h4_ks(M, kt);
     std::vector<uint16_t> ia((size_t)2 * ks * 128 * 8), is((size_t)2 * ks * 128 * 8);
-    pqmf::hankel4_build_banks(hk_host, M, L, jlo, kt, ia.data(), is.data());
-    uint16_t* imgp = reinterpret_cast<uint16_t*>(tables_host);
-    pqmf::hankel4_pair_image(ia.data(), ks, imgp);
-    pqmf::hankel4_pair_image(is.data(), ks, imgp + 2 * h4_pair_floats(M, L));
-    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt, false, 4e-6);
-    const int trim_s = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt, true, 9e-6);
+    if (!split) {
+      pqmf::hankel4_build_banks(hk_host, M, L, jlo, kt, ia.data(), is.data());
+      pqmf::hankel4_pair_image(ia.data(), ks, base);
+      pqmf::hankel4_pair_image(is.data(), ks, base + 2 * h4_pair_floats(M, L));
+    } else {
+      for (int half = 0; half < 2; ++half) {
+        pqmf::hankel4_build_banks(hk_host, M, L, jlo + half * kt, kt, ia.data(), is.data());
+        pqmf::hankel4_pair_image(ia.data(), ks, base + 2 * (half * h4_half_floats(M, L)));
+        pqmf::hankel4_pair_image(is.data(), ks, base + 2 * ((2 + half) * h4_half_floats(M, L)));
+      }
+    }
+    const int kt_all = split ? 2 * kt : kt;
+    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, false, 4e-6);
+    const int trim_s = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, true, 9e-6);
     if (residual) *residual = 0.0;
-    if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s);
+    if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s) | (split ? PQMF_FLAG_H4_SPLIT : 0u);
     return PQMF_OK;
   }
   std::memset(tables_host, 0, (size_t)pqmf_tables_numel(M, L) * sizeof(float));

@@ -358,19 +358,24 @@ def test_hankel_other_band_counts_vs_oracle(golden, pq, m, b, frames):
     assert np.abs(oc[:, 0] - O.synthesis(s, hk, delay_frames=1)).max() <= TOL / 2
 
 
-@pytest.mark.parametrize("att,m", ((60, 16), (140, 16), (60, 32), (140, 8), (60, 8), (80, 16)))
+@pytest.mark.parametrize("att,m", ((60, 16), (140, 16), (60, 32), (140, 8), (60, 8), (80, 16), (100, 64), (120, 32), (60, 64)))
 def test_hankel_other_prototype_lengths(pq, att, m):
-    """Prototype lengths other than 32 n_band (L = 16 M or 64 M): tap span, K-steps and trims come from the actual bank."""
+    """Prototype lengths other than 32 n_band (L = 16 M or 64 M): tap span, K-steps and trims come from the actual bank.  Banks too
+    long for one SM's shared memory (n_band 64; attenuation 120 at n_band 32) run as two tap ranges, the second launch accumulating."""
     mod = pq.PQMF(att, m).cuda()
     assert mod._tables.numel() > 0
     hk = mod.hk.cpu().numpy()
     b, t = 24, 32768
     x = O.audio_like((b, 1, t), att + m)
+    tol = TOL / 2 if m < 64 else TOL  # at n_band 64 fp32 accumulation of 64 x 24 products with gain 64 alone is ~4e-6 (any fp32 path)
     y = mod(dev(x)).cpu().numpy()
     y64 = O.analysis(x[:, 0], hk)
     assert np.abs(y - y64).max() <= TOL / 2
     s = y64.astype(np.float32)
     out = mod.inverse(dev(s)).cpu().numpy()
-    assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
+    assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= tol
     ex = pq.PQMF(att, m, exact=True).cuda()
     assert (ex(dev(x)).cpu().numpy() - y).__abs__().max() <= 3e-6
+    cached = pq.CachedPQMF(att, m).cuda()
+    oc = cached.inverse(dev(s)).cpu().numpy()
+    assert np.abs(oc[:, 0] - O.synthesis(s, hk, delay_frames=1)).max() <= tol

@@ -161,14 +161,15 @@ def test_product_never_imports_the_oracle():
 
 def test_tables_exist_for_the_tensor_core_band_counts_and_degrade_gracefully():
     """n_band 8 / 16 / 32 get tensor-core tables (with the tap span and trim facts in the flags); banks the kernels cannot hold
-    (n_band 32 at attenuation 120: 1024 taps) and other band counts fall back to the direct form instead of raising."""
+    (n_band 64 at attenuation 120) and other band counts fall back to the direct form instead of raising."""
     import pqmf_b200 as pq
 
+    assert (pq.PQMF(100, 64)._flags >> 23) & 1 and (pq.PQMF(120, 32)._flags >> 23) & 1  # split into two tap ranges
     for m, jlo, kt in ((8, 32, 192), (16, 64, 384), (32, 128, 768)):
         mod = pq.PQMF(100, m)
         assert mod._tables.numel() > 0
         assert 32 * ((mod._flags >> 8) & 15) == jlo and 32 * ((mod._flags >> 12) & 31) == kt
         assert 0 < ((mod._flags >> 17) & 7) <= 7 and 0 < ((mod._flags >> 20) & 7) <= 7
-    for att, m in ((120, 32), (100, 4), (100, 64), (100, 2)):
+    for att, m in ((120, 64), (100, 4), (100, 2)):
         mod = pq.PQMF(att, m)
         assert mod._tables.numel() == 0 and (mod._flags >> 8) == 0
