@@ -379,3 +379,18 @@ def test_hankel_other_prototype_lengths(pq, att, m):
     cached = pq.CachedPQMF(att, m).cuda()
     oc = cached.inverse(dev(s)).cpu().numpy()
     assert np.abs(oc[:, 0] - O.synthesis(s, hk, delay_frames=1)).max() <= tol
+
+
+def test_cta_pair_and_single_cta_kernels_are_bit_identical(pq, lib):
+    """PQMF_FLAG_NO_PAIR selects the one-CTA-per-SM launch of the same kernels: identical arithmetic, identical bits (odd tile
+    counts exercise the pair's padding tile)."""
+    mod = pq.PQMF(100, 16).cuda()
+    torch.manual_seed(3)
+    for b, frames in ((25, 2564), (97, 516), (1, 512 * 97)):
+        x = (0.5 * torch.randn(b, 1, 16 * frames, device="cuda")).clamp_(-1, 1)
+        y_pair = torch.ops.pqmf_b200.analysis(x, mod.hk, mod._tables, frames, mod._flags)
+        y_one = torch.ops.pqmf_b200.analysis(x, mod.hk, mod._tables, frames, mod._flags | lib.PQMF_FLAG_NO_PAIR)
+        assert torch.equal(y_pair, y_one)
+        o_pair = torch.ops.pqmf_b200.synthesis(y_one, mod.hk, mod._tables, 0, mod._flags)
+        o_one = torch.ops.pqmf_b200.synthesis(y_one, mod.hk, mod._tables, 0, mod._flags | lib.PQMF_FLAG_NO_PAIR)
+        assert torch.equal(o_pair, o_one)
