@@ -43,6 +43,7 @@ extern "C" {
                               * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
 
 #define PQMF_FLAG_NO_PAIR 8u /* n_band 16 offline kernels: one CTA per SM instead of CTA pairs (measurement / debugging)              */
+#define PQMF_FLAG_NO_FOLD 32u /* n_band 16: never use the fold + modulation kernels (a bank that is not window x cosine: the Hankel kernels take hk as it is) */
 #define PQMF_FLAG_FOLD 4u    /* n_band 16 only: force the fold + modulation kernels (the streaming kernels) offline too */
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* from pqmf_build_tables_f32 */
 /* from pqmf_build_tables_f32: edge K-steps (analysis, synthesis) of the offline n_band 16 kernels whose fp16 correction

@@ -23,6 +23,7 @@ PQMF_FLAG_EXACT = 1
 PQMF_FLAG_NO_SIGN = 2
 PQMF_FLAG_FOLD = 4
 PQMF_FLAG_NO_PAIR = 8
+PQMF_FLAG_NO_FOLD = 32
 PQMF_FLAG_H4_SPLIT = 1 << 23
 
 

@@ -299,7 +299,7 @@ int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, 
     const int e = h4_analysis(x, y, tables, B, T, F, 16, 512, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) return e;
   }
-  if (flags & PQMF_FLAG_EXACT) return exact_tc_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
+  if (flags & (PQMF_FLAG_EXACT | PQMF_FLAG_NO_FOLD)) return exact_tc_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
   return pqmf::fast16_analysis(x, hist, y, hist_out, tables, B, T, F, off, parity, flags, st);
 }
 
@@ -309,7 +309,7 @@ int fast_synthesis(const float* s, const float* hist, float* out, float* hist_ou
     const int e = h4_synthesis(s, out, tables, B, F, off2, 16, 512, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) return e;
   }
-  if (flags & PQMF_FLAG_EXACT) return exact_tc_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
+  if (flags & (PQMF_FLAG_EXACT | PQMF_FLAG_NO_FOLD)) return exact_tc_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
   return pqmf::fast16_synthesis(s, hist, out, hist_out, tables, B, F, off2, parity, flags, st);
 }
 

@@ -89,7 +89,8 @@ class PQMF(nn.Module):
     polyphase   : kept for API compatibility -- both settings run the same fused kernel and differ only in
                   the shape checks the reference applies (polyphase needs T % n_band == 0)
     n_channels  : stored, as in the reference; multichannel input is folded into the batch
-    exact       : force the direct-form kernels (bit-faithful to ``hk``) instead of the fold + tensor-core path
+    exact       : every term of the registered ``hk`` (Hankel-16 tensor-core kernels at n_band 16, register-tiled direct form
+                  elsewhere) instead of the default kernels, whose error is bounded below the 1e-5 tolerance
     """
 
     def __init__(self, attenuation, n_band, polyphase=True, n_channels=1, exact=False):
@@ -116,9 +117,11 @@ class PQMF(nn.Module):
         """(Re)derive the fast-path coefficient tables from the current ``hk`` / ``h`` buffers."""
         tables, residual, fast_flags = _lib.build_tables(self.hk, self.h)
         if tables.numel() and not (residual <= _FOLD_RESIDUAL_LIMIT):
-            tables, fast_flags = torch.zeros(0), 0  # bank is not window x cosine: stay on the direct form
+            # bank is not window x cosine (e.g. a hand-edited hk was loaded): the fold + modulation kernels do not apply, the
+            # Hankel kernels (which take hk as it is) still do
+            fast_flags |= _lib.PQMF_FLAG_NO_FOLD
         self.fold_residual = residual
-        self._flags = (self._flags & 0xFF) | fast_flags
+        self._flags = (self._flags & _lib.PQMF_FLAG_EXACT) | fast_flags
         self._tables = tables.to(self.hk.device)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

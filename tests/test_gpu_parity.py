@@ -394,3 +394,24 @@ def test_cta_pair_and_single_cta_kernels_are_bit_identical(pq, lib):
         o_pair = torch.ops.pqmf_b200.synthesis(y_one, mod.hk, mod._tables, 0, mod._flags)
         o_one = torch.ops.pqmf_b200.synthesis(y_one, mod.hk, mod._tables, 0, mod._flags | lib.PQMF_FLAG_NO_PAIR)
         assert torch.equal(o_pair, o_one)
+
+
+def test_custom_bank_that_is_not_window_times_cosine(golden, pq):
+    """A hand-edited hk (loaded through the state dict) breaks the fold factorisation; the module then keeps the Hankel kernels,
+    which take hk as it is, for both the streaming-size and the offline-batch paths."""
+    hk = golden("bank_M16.npz")["hk"].copy()
+    rng = np.random.default_rng(0)
+    hk[:, 100:400] *= (1.0 + 0.05 * rng.standard_normal((16, 300))).astype(np.float32)
+    mod = pq.PQMF(100, 16).cuda()
+    sd = mod.state_dict()
+    sd["hk"] = torch.from_numpy(hk)
+    mod.load_state_dict(sd)
+    assert mod.fold_residual > 1e-6 and mod._tables.numel() > 0
+    for b, t in ((2, 16 * 600), (24, 32768)):
+        x = O.audio_like((b, 1, t), 3 + b)
+        y = mod(dev(x)).cpu().numpy()
+        y64 = O.analysis(x[:, 0], hk)
+        assert np.abs(y - y64).max() <= TOL / 2
+        s = y64.astype(np.float32)
+        out = mod.inverse(dev(s)).cpu().numpy()
+        assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
