@@ -221,6 +221,7 @@ struct H4AnalysisParams {
   int parity;
   int trim_lo, trim_hi;  // edge K-steps without correction terms (h4_issue_mmas)
   int accumulate;        // add to what y already holds (second launch of a bank split in two tap ranges)
+  int keep_in_l2;        // store y without the streaming hint: a synthesis launch that follows walks the tiles backwards and finds the tail in L2
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -341,7 +342,11 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
           float* q = yp + (size_t)kk * p.F;
           if constexpr (FR >= 4) {
 #pragma unroll
-            for (int d4 = 0; d4 < FR; d4 += 4) __stcs(reinterpret_cast<float4*>(q + d4), make_float4(v[d4][kk], v[d4 + 1][kk], v[d4 + 2][kk], v[d4 + 3][kk]));
+            for (int d4 = 0; d4 < FR; d4 += 4) {
+              const float4 w = make_float4(v[d4][kk], v[d4 + 1][kk], v[d4 + 2][kk], v[d4 + 3][kk]);
+              if (p.keep_in_l2) *reinterpret_cast<float4*>(q + d4) = w;
+              else __stcs(reinterpret_cast<float4*>(q + d4), w);
+            }
           } else if constexpr (FR == 2) {
             __stcs(reinterpret_cast<float2*>(q), make_float2(v[0][kk], v[1][kk]));
           } else {
@@ -411,6 +416,7 @@ struct H4SynthesisParams {
   int parity;
   int trim_lo, trim_hi;
   int accumulate;        // add to what out already holds
+  int reverse;           // walk the tiles from the last to the first (see H4AnalysisParams::keep_in_l2)
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -455,6 +461,10 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     const bool has_item = tid < n_fq * NBG;
     float4 v0[8];  // prefetched one tile ahead
     auto load_frames = [&](float4 (&v)[8], unsigned bb, unsigned cc) {
+      if (p.reverse && bb < n_rows) {
+        bb = n_rows - 1 - bb;
+        cc = tpr - 1 - cc;
+      }
       const long n = (long)cc * (kH4Rows * FR) + nbase + 4 * fq;
       const float* sp = p.s + ((size_t)bb * M + 8 * bg) * p.F + n;
       const bool ok = bb < n_rows && has_item && n >= 0 && n + 3 < p.F;
@@ -497,6 +507,10 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     // apart: stored like that, every warp store would touch 32 lines.  A 4 x 4 chunk transpose inside each lane quad (two shuffle
     // stages) leaves lane r with chunk r & 3 of the quad's four rows, so one STG.256 covers eight whole 128-byte lines.
     auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
+      if (p.reverse) {
+        bb = n_rows - 1 - bb;
+        cc = tpr - 1 - cc;
+      }
       const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
       const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);

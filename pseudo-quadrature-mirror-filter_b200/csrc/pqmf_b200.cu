@@ -207,7 +207,7 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   h4_taps(flags, jlo, kt);
   if (kt == 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4AnalysisParams p{};
-  p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0;
+  p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.keep_in_l2 = 1;
   switch (M) {
     case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, L, flags, st);
     case 16: return h4_analysis_m<16>(p, tables, jlo, kt, B, L, flags, st);
@@ -254,7 +254,7 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
   h4_taps(flags, jlo, kt);
   if (kt == 0 || off2 % M != 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisParams p{};
-  p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0;
+  p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0; p.reverse = 1;
   switch (M) {
     case 8: return h4_synthesis_m<8>(p, tables, jlo, kt, B, L, flags, st);
     case 16: return h4_synthesis_m<16>(p, tables, jlo, kt, B, L, flags, st);
