@@ -111,6 +111,14 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
                               float* state_out, int B, long n_frames, int M, int L, int frame_parity, unsigned flags,
                               pqmf_stream_t stream);
 
+/* ---- fused round trip on device buffers: PQMFWrapper.process (PQMFWrapper.py:81-92: forward, then inverse of the same
+ *      sub-bands) and the Pvoc wrapper's forward (1-PitchShifterWrapper.py:303-316) ----
+ * pqmf_analysis_f32 followed by pqmf_synthesis_f32 on the same stream, as one call; the synthesis kernels walk their tiles
+ * last-to-first, so the most recently written part of y is still in L2 when it is read back.  x [B, T] -> y [B, M, n_frames]
+ * (required: the sub-bands are an output of process()) and out [B, M * n_frames].  n_frames as for pqmf_analysis_f32. */
+int pqmf_roundtrip_f32(const float* x, float* y, float* out, const float* hk, const float* tables, int B, long T, long n_frames,
+                       int M, int L, int delay_frames, unsigned flags, pqmf_stream_t stream);
+
 /* ---- end-to-end host entry (what a non-torch host -- e.g. the Pure Data external that loads the
  *      reference's .ts, README.md:16 -- would call): host buffers in, host buffers out.
  * Pipelines H2D copy, analysis, synthesis and D2H copy over row chunks on internal streams and

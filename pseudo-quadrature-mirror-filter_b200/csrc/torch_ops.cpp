@@ -82,6 +82,26 @@ at::Tensor synthesis(const at::Tensor& s, const at::Tensor& hk, const at::Tensor
   return out;
 }
 
+// x [B, C, T] -> (out [B, C, M*n_frames], y [B, C*M, n_frames]): forward then inverse in one call (pqmf_roundtrip_f32)
+std::tuple<at::Tensor, at::Tensor> roundtrip(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames,
+                                             int64_t delay_frames, int64_t flags) {
+  check_f32_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 3, "pqmf roundtrip expects [batch, channels, time], got ", x.dim(), " dims");
+  const Bank bank = bank_of(hk, x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const at::Tensor xc = x.contiguous();
+  const int64_t B = xc.size(0) * xc.size(1), T = xc.size(2);
+  TORCH_CHECK(n_frames >= 0 && B < (1LL << 31), "bad sizes");
+  at::Tensor y = at::empty({xc.size(0), xc.size(1) * bank.M, n_frames}, xc.options());
+  at::Tensor out = at::empty({xc.size(0), xc.size(1), bank.M * n_frames}, xc.options());
+  if (y.numel() == 0) return {out, y};
+  check_rc(pqmf_roundtrip_f32(xc.data_ptr<float>(), y.data_ptr<float>(), out.data_ptr<float>(), bank.ptr, tables_ptr(tables, x), (int)B,
+                              (long)T, (long)n_frames, (int)bank.M, (int)bank.L, (int)delay_frames, (unsigned)flags,
+                              (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_roundtrip_f32");
+  return {out, y};
+}
+
 // streaming: state tensors are caller-owned ping-pong buffers; state_out is written in place.
 at::Tensor analysis_stream(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& state_in,
                            at::Tensor state_out, int64_t frame_parity, int64_t flags) {
@@ -218,6 +238,7 @@ TORCH_LIBRARY(pqmf_b200, m) {
   m.def(
       "synthesis_stream(Tensor s, Tensor hk, Tensor tables, Tensor state_in, Tensor(a!) state_out, int frame_parity, int flags) "
       "-> Tensor");
+  m.def("roundtrip(Tensor x, Tensor hk, Tensor tables, int n_frames, int delay_frames, int flags) -> (Tensor, Tensor)");
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -226,6 +247,7 @@ TORCH_LIBRARY_IMPL(pqmf_b200, CUDA, m) {
   m.impl("synthesis", &synthesis);
   m.impl("analysis_stream", &analysis_stream);
   m.impl("synthesis_stream", &synthesis_stream);
+  m.impl("roundtrip", &roundtrip);
 }
 
 // gradients w.r.t. the signal / the sub-bands only (the bank is a registered buffer in the reference, not a parameter)

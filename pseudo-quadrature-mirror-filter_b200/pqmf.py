@@ -18,6 +18,8 @@ from __future__ import annotations
 
 import math
 
+from typing import Tuple
+
 import torch
 import torch.nn as nn
 
@@ -145,6 +147,23 @@ class PQMF(nn.Module):
             return x
         return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 0, self._flags)
 
+    @torch.jit.export
+    def process(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(inverse(forward(x)), forward(x))`` -- what the reference's ``PQMFWrapper.process`` computes (PQMFWrapper.py:81-92) --
+        in one op (bit-identical to the two calls; the synthesis kernel walks its tiles last-to-first, so the tail of the
+        sub-bands is read back from L2).  Under autograd it falls back to ``forward`` / ``inverse``."""
+        if x.dim() != 3:
+            raise RuntimeError("PQMF.process expects a 3-D tensor [batch, channels, time]")
+        if self.n_band == 1:
+            return x, x
+        t = x.shape[-1]
+        if self.polyphase and t % self.n_band != 0:
+            raise RuntimeError("polyphase PQMF needs the number of samples to be a multiple of n_band")
+        if torch.is_grad_enabled() and x.requires_grad:  # the fused op has no autograd kernel: same result through the two ops
+            y = self.forward(x)
+            return self.inverse(y), y
+        return torch.ops.pqmf_b200.roundtrip(x, self.hk, self._tables, t // self.n_band, 0, self._flags)
+
 
 class _BankConv(nn.Module):
     """Weight holder standing in for the two ``cached_conv.Conv1d`` layers of the reference's CachedPQMF
@@ -230,6 +249,20 @@ class CachedPQMF(PQMF):
         if self.streaming:
             return self.inverse_stream(x)
         return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 1, self._flags)
+
+    @torch.jit.export
+    def process(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Offline ``(inverse(forward(x)), forward(x))`` in one op (see ``PQMF.process``); the reconstruction is one frame late,
+        as ``CachedPQMF.inverse``."""
+        if x.dim() != 3:
+            raise RuntimeError("CachedPQMF.process expects a 3-D tensor [batch, channels, time]")
+        if self.n_band == 1:
+            return x, x
+        if torch.is_grad_enabled() and x.requires_grad:
+            y = self.forward(x)
+            return self.inverse(y), y
+        n_frames = (x.shape[-1] + self.n_band - 1) // self.n_band
+        return torch.ops.pqmf_b200.roundtrip(x, self.hk, self._tables, n_frames, 1, self._flags)
 
     @torch.jit.export
     def forward_stream(self, x: torch.Tensor) -> torch.Tensor:

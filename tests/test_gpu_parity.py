@@ -415,3 +415,24 @@ def test_custom_bank_that_is_not_window_times_cosine(golden, pq):
         s = y64.astype(np.float32)
         out = mod.inverse(dev(s)).cpu().numpy()
         assert np.abs(out[:, 0] - O.synthesis(s, hk)).max() <= TOL / 2
+
+
+@pytest.mark.parametrize("m,b,t", ((16, 64, 1 << 18), (16, 3, 16 * 1000), (8, 40, 8 * 8192), (32, 5, 32 * 300), (16, 200, 16 * 2048)))
+def test_fused_process_equals_forward_then_inverse(pq, m, b, t):
+    """process() = forward() then inverse() as one op (PQMFWrapper.process): the same bits, for every kernel path."""
+    torch.manual_seed(m + b)
+    x = (0.5 * torch.randn(b, 1, t, device="cuda")).clamp_(-1, 1)
+    for cls, ragged in ((pq.PQMF, 0), (pq.CachedPQMF, 5)):
+        mod = cls(100, m).cuda()
+        xs = x[..., : t - ragged].contiguous() if ragged else x
+        y = mod(xs)
+        out = mod.inverse(y)
+        out_f, y_f = mod.process(xs)
+        assert torch.equal(y, y_f) and torch.equal(out, out_f)
+        scripted = torch.jit.script(mod)
+        out_s, y_s = scripted.process(xs)
+        assert torch.equal(out_s, out) and torch.equal(y_s, y)
+    xg = x[:2].clone().requires_grad_(True)
+    out_g, _ = mod.process(xg)  # falls back to the differentiable ops
+    out_g.square().sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
