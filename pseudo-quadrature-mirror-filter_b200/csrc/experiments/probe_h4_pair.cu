@@ -24,11 +24,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// cluster_ctarank() / cluster_sync_all() now live in ../ptx.cuh
 __device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
