@@ -18,6 +18,7 @@
 #include "fast16_synth.cuh"
 #include "hankel16.cuh"
 #include "hankel4.cuh"
+#include "hankel4_stream.cuh"
 
 namespace {
 
@@ -262,6 +263,52 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
     case 64: return h4_synthesis_m<64>(p, tables, jlo, kt, B, L, flags, st);
     default: return PQMF_ERR_UNSUPPORTED;
   }
+}
+
+// ---- streaming blocks of n_band 16 on the Hankel kernels (hankel4_stream.cuh): several streams per MMA tile.  Any refusal
+//      (short blocks, few streams, odd sizes, a context without CTA pairs) returns UNSUPPORTED and the fold kernels run instead ----
+int h4_analysis_stream(const float* x, float* y, const float* tables, const float* state_in, float* state_out, int B, long T, int L,
+                       int parity, unsigned flags, cudaStream_t st) {
+  int jlo, kt;
+  h4_taps(flags, jlo, kt);
+  if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_EXACT | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
+  if ((L - jlo) % 64 != 0 || T % 256 != 0 || T < L) return PQMF_ERR_UNSUPPORTED;
+  const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(T, L - jlo);
+  if (sg.pitch > pqmf::kH4Rows || sg.spt < 1 || (B + sg.spt - 1) / sg.spt < 96) return PQMF_ERR_UNSUPPORTED;
+  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)state_in | (uintptr_t)state_out) % 16) return PQMF_ERR_UNSUPPORTED;
+  pqmf::H4AnalysisStreamParams p{};
+  p.x = x; p.hist_in = state_in; p.hist_out = state_out; p.y = y; p.T = T; p.B = B; p.L = L; p.parity = parity & 1;
+  p.trim_lo = p.trim_hi = (int)((flags >> 17) & 7u);
+  p.g = pqmf::h4_shape(16, jlo, kt, true, false);
+  p.s = sg;
+  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset);
+  if (pqmf::h4_launch_analysis_stream(p, st) != 0) {
+    (void)cudaGetLastError();
+    return PQMF_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+int h4_synthesis_stream(const float* s, float* out, const float* tables, const float* state_in, float* state_out, int B, long F, int L,
+                        int parity, unsigned flags, cudaStream_t st) {
+  int jlo, kt;
+  h4_taps(flags, jlo, kt);
+  if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_EXACT | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
+  const int K = L / 16, hist_frames = (jlo + kt) / 16;  // = ehi + 1: with o = -1 the window of output frame f starts at sub-band frame f - hist_frames
+  if (hist_frames % 4 != 0 || hist_frames > K || F % 16 != 0 || F < K) return PQMF_ERR_UNSUPPORTED;
+  const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(F * 16, hist_frames * 16);
+  if (sg.pitch > pqmf::kH4Rows || sg.spt < 1 || (B + sg.spt - 1) / sg.spt < 96) return PQMF_ERR_UNSUPPORTED;
+  if (((uintptr_t)s | (uintptr_t)state_in | (uintptr_t)state_out) % 16 || ((uintptr_t)out % 32)) return PQMF_ERR_UNSUPPORTED;
+  pqmf::H4SynthesisStreamParams p{};
+  p.s = s; p.state_in = state_in; p.state_out = state_out; p.out = out; p.F = F; p.B = B; p.K = K; p.parity = parity & 1;
+  p.trim_lo = p.trim_hi = (int)((flags >> 20) & 7u);
+  p.g = pqmf::h4_shape(16, jlo, kt, true, true);
+  p.sg = sg;
+  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset + kH4PairImageFloats);
+  if (pqmf::h4_launch_synthesis_stream(p, st) != 0) {
+    (void)cudaGetLastError();
+    return PQMF_ERR_UNSUPPORTED;
+  }
+  return 0;
 }
 
 // n_band 16 fast path: fold + tensor-core modulation (fast16*.cuh), or -- with PQMF_FLAG_EXACT -- the direct form as an
@@ -510,6 +557,7 @@ int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const long F = T / M;
   if (use_fast(M, L, tables, flags) && pqmf::hankel16_analysis_ok(x, y, T, F)) {
+    if (h4_analysis_stream(x, y, tables, state_in, state_out, B, T, L, frame_parity, flags, st) == 0) { ++g_launches; return 0; }
     int e = fast_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
@@ -529,6 +577,7 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
   const int K = L / M;
   // history frames sit K frames before frame 0 of the block: their parity offset is (frame_parity - K)
   if (use_fast(M, L, tables, flags) && pqmf::hankel16_synthesis_ok(s, out, n_frames)) {
+    if (h4_synthesis_stream(s, out, tables, state_in, state_out, B, n_frames, L, frame_parity, flags, st) == 0) { ++g_launches; return 0; }
     int e = fast_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }

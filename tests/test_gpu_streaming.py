@@ -85,3 +85,34 @@ def test_config3_many_streams(pq):
     err = out_s[..., lat:] - x[..., :-lat]
     snr = 10 * torch.log10((x[..., :-lat] ** 2).sum() / (err ** 2).sum())
     assert snr.item() > 30.0
+
+
+@pytest.mark.parametrize("streams,block,exact_bank", ((300, 2048, False), (1000, 512, False), (290, 4096, False), (97, 7680, False), (299, 1024, False),
+                                                      (300, 2048, True)))
+def test_many_streams_on_the_hankel_kernels(golden, pq, streams, block, exact_bank):
+    """>= 96 tiles of streams: the streaming blocks run on the tensor-core Hankel kernels (several streams per MMA tile, history rows
+    in front of every block, state rolled by the loader threads).  Checked against the float64 streaming oracle, against the fold
+    kernels (PQMF_FLAG_FOLD) and against the offline result."""
+    from pqmf_b200 import _lib
+
+    att = 120 if exact_bank else 100  # attenuation 120: no zero taps -> 8 history rows instead of 7
+    mod = pq.CachedPQMF(att, 16).cuda()
+    hk = mod.hk.cpu().numpy()
+    n_blocks = 3
+    t = n_blocks * block
+    x = O.audio_like((streams, 1, t), 5 + block)
+    xd = torch.from_numpy(x).cuda()
+    y_s, out_s = _run_stream(mod, xd, block)
+    st = O.StreamState(streams, 16, 512)
+    y64 = O.stream_analysis(x[:, 0], hk, st)
+    o64 = O.stream_synthesis(y_s.cpu().numpy(), hk, st)
+    assert np.abs(y_s.cpu().numpy() - y64).max() <= TOL / 2
+    assert np.abs(out_s.cpu().numpy()[:, 0] - o64).max() <= TOL / 2
+    # the fold kernels on the same blocks
+    fold = pq.CachedPQMF(att, 16).cuda()
+    fold._flags |= _lib.PQMF_FLAG_FOLD
+    y_f, out_f = _run_stream(fold, xd, block)
+    assert (y_f - y_s).abs().max().item() <= 3e-6 and (out_f - out_s).abs().max().item() <= 8e-6
+    # state really is carried: the streamed sub-bands equal the offline ones of the zero-prefixed signal
+    xz = torch.cat([torch.zeros(streams, 1, 256, device="cuda"), xd], dim=-1)
+    assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 3e-6
