@@ -38,7 +38,8 @@ extern "C" {
 #define PQMF_ERR_NO_DEVICE (-3)   /* no CUDA device / wrong architecture (needs sm_100)          */
 
 /* flags */
-#define PQMF_FLAG_EXACT 1u   /* direct form with every term of the registered hk (no fold factorisation, no trimmed steps) */
+#define PQMF_FLAG_EXACT 1u   /* every term of the registered hk: no fold factorisation, no trimmed correction steps (Hankel kernels with
+                              * trim 0 for large batches, Hankel-16 / register-tiled direct form otherwise) */
 #define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
                               * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
 

@@ -174,7 +174,7 @@ void h4_taps(unsigned flags, int& jlo, int& kt) {
 
 template <int M>
 int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
-  const int trim = (int)((flags >> 17) & 7u);
+  const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);  // exact mode: every correction term
   if (flags & PQMF_FLAG_H4_SPLIT) {  // two tap ranges, two launches; only the outer edge of each range may skip the corrections
     for (int half = 0; half < 2; ++half) {
       p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, false);
@@ -220,7 +220,7 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
 
 template <int M>
 int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
-  const int trim = (int)((flags >> 20) & 7u);
+  const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
   if (flags & PQMF_FLAG_H4_SPLIT) {
     for (int half = 0; half < 2; ++half) {
       p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, true);
@@ -271,14 +271,14 @@ int h4_analysis_stream(const float* x, float* y, const float* tables, const floa
                        int parity, unsigned flags, cudaStream_t st) {
   int jlo, kt;
   h4_taps(flags, jlo, kt);
-  if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_EXACT | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
+  if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
   if ((L - jlo) % 64 != 0 || T % 256 != 0 || T < L) return PQMF_ERR_UNSUPPORTED;
   const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(T, L - jlo);
   if (sg.pitch > pqmf::kH4Rows || sg.spt < 1 || (B + sg.spt - 1) / sg.spt < 96) return PQMF_ERR_UNSUPPORTED;
   if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)state_in | (uintptr_t)state_out) % 16) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4AnalysisStreamParams p{};
   p.x = x; p.hist_in = state_in; p.hist_out = state_out; p.y = y; p.T = T; p.B = B; p.L = L; p.parity = parity & 1;
-  p.trim_lo = p.trim_hi = (int)((flags >> 17) & 7u);
+  p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);
   p.g = pqmf::h4_shape(16, jlo, kt, true, false);
   p.s = sg;
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset);
@@ -292,7 +292,7 @@ int h4_synthesis_stream(const float* s, float* out, const float* tables, const f
                         int parity, unsigned flags, cudaStream_t st) {
   int jlo, kt;
   h4_taps(flags, jlo, kt);
-  if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_EXACT | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
+  if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
   const int K = L / 16, hist_frames = (jlo + kt) / 16;  // = ehi + 1: with o = -1 the window of output frame f starts at sub-band frame f - hist_frames
   if (hist_frames % 4 != 0 || hist_frames > K || F % 16 != 0 || F < K) return PQMF_ERR_UNSUPPORTED;
   const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(F * 16, hist_frames * 16);
@@ -300,7 +300,7 @@ int h4_synthesis_stream(const float* s, float* out, const float* tables, const f
   if (((uintptr_t)s | (uintptr_t)state_in | (uintptr_t)state_out) % 16 || ((uintptr_t)out % 32)) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisStreamParams p{};
   p.s = s; p.state_in = state_in; p.state_out = state_out; p.out = out; p.F = F; p.B = B; p.K = K; p.parity = parity & 1;
-  p.trim_lo = p.trim_hi = (int)((flags >> 20) & 7u);
+  p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
   p.g = pqmf::h4_shape(16, jlo, kt, true, true);
   p.sg = sg;
   p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset + kH4PairImageFloats);
@@ -342,7 +342,7 @@ int exact_tc_synthesis(const float* s, const float* hist, float* out, float* his
 
 int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, const float* tables, int B, long T, long F, int off,
                   int parity, unsigned flags, cudaStream_t st) {
-  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, 16, hist) && h4_analysis_ok(x, y, T, F, 16) && off == 256) {
+  if (!(flags & PQMF_FLAG_FOLD) && use_h4(B, F, 16, hist) && h4_analysis_ok(x, y, T, F, 16) && off == 256) {
     const int e = h4_analysis(x, y, tables, B, T, F, 16, 512, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) return e;
   }
@@ -352,7 +352,7 @@ int fast_analysis(const float* x, const float* hist, float* y, float* hist_out, 
 
 int fast_synthesis(const float* s, const float* hist, float* out, float* hist_out, const float* tables, int B, long F, int off2,
                    int parity, unsigned flags, cudaStream_t st) {
-  if (!(flags & (PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && use_h4(B, F, 16, hist) && h4_synthesis_ok(s, out, F)) {
+  if (!(flags & PQMF_FLAG_FOLD) && use_h4(B, F, 16, hist) && h4_synthesis_ok(s, out, F)) {
     const int e = h4_synthesis(s, out, tables, B, F, off2, 16, 512, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) return e;
   }
@@ -363,9 +363,10 @@ int fast_synthesis(const float* s, const float* hist, float* out, float* hist_ou
 bool use_fast(int M, int L, const float* tables, unsigned flags) {
   return tables != nullptr && !(flags & PQMF_FLAG_NO_SIGN) && pqmf::hankel16_supported(M, L);
 }
-// n_band 8 / 32: only the offline Hankel kernels exist (exact mode, streaming and the sign-less free functions use the direct form)
+// other band counts / prototype lengths: only the offline Hankel kernels exist (streaming, small batches and the sign-less free
+// functions use the direct form); PQMF_FLAG_EXACT keeps them but runs every correction term
 bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
-  return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_EXACT | PQMF_FLAG_FOLD)) && h4_family(M, L);
+  return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_FOLD)) && h4_family(M, L);
 }
 
 }  // namespace
