@@ -116,3 +116,21 @@ def test_many_streams_on_the_hankel_kernels(golden, pq, streams, block, exact_ba
     # state really is carried: the streamed sub-bands equal the offline ones of the zero-prefixed signal
     xz = torch.cat([torch.zeros(streams, 1, 256, device="cuda"), xd], dim=-1)
     assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 3e-6
+
+
+def test_config3_sixty_four_steps_equal_offline(pq):
+    """64 consecutive 2048-sample blocks with carried state equal the offline result on the concatenated
+    131 072-sample signal (sub-bands of the zero-prefixed input; reconstruction after the fixed 528-sample latency)."""
+    torch.manual_seed(64)
+    streams, block, n_blocks = 300, 2048, 64
+    mod = pq.CachedPQMF(100, 16).cuda()
+    x = (0.5 * torch.randn(streams, 1, block * n_blocks, device="cuda")).clamp_(-1, 1)
+    y_s, out_s = _run_stream(mod, x, block)
+    xz = torch.cat([torch.zeros(streams, 1, 256, device="cuda"), x], dim=-1)
+    assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 2e-6
+    sz = torch.cat([torch.zeros(streams, 16, 16, device="cuda"), y_s], dim=-1)
+    assert (out_s - mod.inverse(sz)[..., : out_s.shape[-1]]).abs().max().item() <= 4e-6
+    lat = mod.cumulative_delay
+    assert lat == 528
+    err = out_s[..., lat:] - x[..., :-lat]
+    assert (10 * torch.log10((x[..., :-lat] ** 2).sum() / (err ** 2).sum())).item() > 55.0
