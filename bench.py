@@ -271,6 +271,10 @@ def run_gpu(args):
         "per_kernel": {k: {"ms": round(v["ms"], 4), "achieved_gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4)} for k, v in kernels.items()},
         "round_trip_frac": round(2 * algo_bytes / ((t_an + t_sy) * 1e-3) * 1e-9 / peak, 4),
     }
+    # ---- informational: the same kernels outside the power-capped steady state, and the other BASELINE configs (not the metric)
+    other = None
+    if n_gpus == 1:
+        other = other_configs(torch, pq, mod, x, BATCH * N_SAMPLES, peak)
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         cb, cr = 8, 5
@@ -291,11 +295,61 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "other_configs": other,
     }
     print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
     return 0
+
+
+def other_configs(torch, pq, mod, x, n_samples, peak):
+    """Burst timing (6 launches per timed interval, best of 5: the board has not reached its power cap yet) of the headline
+    round trip, n_band 8 / 32 / 64 at the same shape, and config 3 (4096 streams x 2048-sample blocks, state carried)."""
+    def burst(fn, n=5, inner=6):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(n):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(inner):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / inner)
+        return best
+
+    out = {"note": "informational, burst-timed (not the metric): Msamples/s and fraction of the HBM roofline (16 B/sample round trip)"}
+    torch.cuda.synchronize()
+    time.sleep(1.0)  # let the board leave the power-capped state of the main loop
+    try:
+        y = mod(x)
+        ta, ts = burst(lambda: mod(x)), burst(lambda: mod.inverse(y))
+        out["n_band16_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n_samples / (ta + ts) * 1e-3, 1),
+                                 "frac": round(16 * n_samples / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
+        del y
+        for m in (8, 32, 64):
+            bank = pq.PQMF(100, m).to(x.device)
+            ym = bank(x)
+            ta, ts = burst(lambda: bank(x), 3, 4), burst(lambda: bank.inverse(ym), 3, 4)
+            out[f"n_band{m}_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n_samples / (ta + ts) * 1e-3, 1),
+                                       "frac": round(16 * n_samples / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
+            del ym, bank
+        cached = pq.CachedPQMF(100, 16).to(x.device)
+        xs = x.reshape(-1)[: 4096 * 2048].reshape(4096, 1, 2048).contiguous()
+
+        def step():
+            cached.inverse_stream(cached.forward_stream(xs))
+
+        tb = burst(step, 5, 20)
+        out["config3_streaming"] = {"streams": 4096, "block": 2048, "ms_per_block_step": round(tb, 4), "round_trip": round(4096 * 2048 / tb * 1e-3, 1),
+                                    "frac_of_20B_per_sample_roofline": round(20 * 4096 * 2048 / (tb * 1e-3) * 1e-9 / peak, 4)}
+    except Exception as exc:  # never let the informational part break the contract line
+        out["error"] = repr(exc)
+    return out
 
 
 def main():
