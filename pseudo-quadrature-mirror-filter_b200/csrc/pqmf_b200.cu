@@ -596,8 +596,6 @@ int pqmf_roundtrip_f32(const float* x, float* y, float* out, const float* hk, co
   // never reads them from HBM) was measured at the bench shape and loses: 16 MB chunks -35 %, 32 MB -19 %, 64 MB -6 %, 128 MB
   // -2 % against the plain pair of launches -- every extra launch pays a pipeline fill and drain on all SMs.  What survives
   // is the hand-off built into the kernels: synthesis walks its tiles last-to-first and finds the tail of y in L2.
-  cudaStream_t st = (cudaStream_t)stream;
-  (void)st;
   int e = pqmf_analysis_f32(x, y, hk, tables, B, T, n_frames, M, L, flags, stream);
   if (e) return e;
   return pqmf_synthesis_f32(y, out, hk, tables, B, n_frames, M, L, delay_frames, flags, stream);
