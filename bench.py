@@ -100,6 +100,21 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(self.period)
 
+    def sample_now(self):
+        """One sample taken by the caller (used while the GPU is still working through the queued steps, so that even a very
+        short timed region has at least one sample under load)."""
+        if not self.ok:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            self.power_w.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def stop(self):
         self._halt.set()
         self.join(timeout=1.0)
@@ -205,6 +220,7 @@ def run_gpu(args):
         ev[k][1].record(stream)
         out = mod.inverse(y)
         ev[k][2].record(stream)
+    sampler.sample_now()  # the launches above only queue work: the GPU is still inside the timed region here
     torch.cuda.synchronize()
     clocks = sampler.stop()
     if distributed:
