@@ -144,6 +144,9 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
     ptx::mbar_init(&s.mma_bar[1], 1);
     ptx::mbar_init(s.bankfull, 1);
     ptx::fence_barrier_init();
+    // the bank image streams in while the TMEM allocation and the barriers below complete
+    ptx::mbar_arrive_expect_tx(s.bankfull, (uint32_t)g.bank);
+    ptx::bulk_g2s(s.bank, reinterpret_cast<const unsigned char*>(bank_images) + (size_t)rank * g.bank, (uint32_t)g.bank, s.bankfull);
   }
   if (warp == 0) {
     if constexpr (PAIR) {
@@ -157,10 +160,6 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
   __syncthreads();
   if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   ptx::tc_fence_after();
-  if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(s.bankfull, (uint32_t)g.bank);
-    ptx::bulk_g2s(s.bank, reinterpret_cast<const unsigned char*>(bank_images) + (size_t)rank * g.bank, (uint32_t)g.bank, s.bankfull);
-  }
   return *s.tmem_slot;
 }
 
