@@ -137,6 +137,7 @@ template <bool PAIR>
 __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& g, const uint16_t* bank_images, uint32_t rank, int worker_warps,
                                                 int tid) {
   const int warp = tid >> 5;
+  ptx::grid_dep_launch();  // the next kernel in the stream may set itself up while this one is still running
   if (tid == 0) {
     ptx::mbar_init(&s.pfull[0], worker_warps * (PAIR ? 2 : 1));
     ptx::mbar_init(&s.pfull[1], worker_warps * (PAIR ? 2 : 1));
@@ -160,6 +161,7 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
   __syncthreads();
   if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   ptx::tc_fence_after();
+  ptx::grid_dep_wait();  // everything above overlapped the previous kernel's tail; its results (and its reads of our outputs) are done now
   return *s.tmem_slot;
 }
 
@@ -633,13 +635,15 @@ inline int h4_launch(Kern kern, Params p, int B, long row_samples, int threads, 
     cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = (size_t)p.g.bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // start-up overlaps the previous kernel's tail (grid_dep_wait)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return (int)cudaLaunchKernelEx(&cfg, kern, p);
   } else {
     kern<<<(unsigned)grid, threads, p.g.bytes, st>>>(p);

@@ -338,13 +338,15 @@ inline int h4_stream_launch(Kern kern, Params p, int threads, int (&configured)[
   cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = (size_t)p.g.bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return (int)cudaLaunchKernelEx(&cfg, kern, p);
 }
 inline int h4_launch_analysis_stream(H4AnalysisStreamParams p, cudaStream_t st) {

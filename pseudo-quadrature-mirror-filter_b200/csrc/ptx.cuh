@@ -212,6 +212,13 @@ __device__ __forceinline__ void umma_pair_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and run
+//      its prologue) while the previous kernel in the stream is still draining; it must execute grid_dep_wait() before it touches
+//      global memory the previous kernel reads or writes.  grid_dep_launch() lets the NEXT kernel do the same with us.  Both are
+//      no-ops for ordinary launches. ----
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- 256-bit streaming global accesses (sm_100: STG.256 / LDG.256); p must be 32-byte aligned ----
 __device__ __forceinline__ void stg256_cs(float* p, const float (&v)[8]) {
   asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
