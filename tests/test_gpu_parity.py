@@ -436,3 +436,20 @@ def test_fused_process_equals_forward_then_inverse(pq, m, b, t):
     out_g, _ = mod.process(xg)  # falls back to the differentiable ops
     out_g.square().sum().backward()
     assert xg.grad is not None and torch.isfinite(xg.grad).all()
+
+
+@pytest.mark.parametrize("scale", (1e-3, 1.0, 300.0, 2.0e4))
+def test_hankel_kernels_are_scale_covariant(golden, pq, scale):
+    """The fp16 two-term split keeps relative accuracy up to the fp16 range (|x| < 65 504): errors scale with the signal.  Downwards
+    there is an absolute floor instead: the second term of a sample below ~0.1 is an fp16 subnormal (step 6e-8), so quiet signals
+    keep ~3e-8 per sample of absolute accuracy (-150 dBFS), not the relative accuracy of fp32."""
+    hk = golden("bank_M16.npz")["hk"]
+    b, t = 24, 32768
+    x = (O.audio_like((b, 1, t), 77) * scale).astype(np.float32)
+    mod = pq.PQMF(100, 16).cuda()
+    y = mod(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0].astype(np.float64), hk)
+    assert np.isfinite(y).all() and np.abs(y - y64).max() <= TOL / 2 * scale + 2e-7
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.isfinite(out).all() and np.abs(out[:, 0] - O.synthesis(s.astype(np.float64), hk)).max() <= TOL / 2 * scale + 1e-6
