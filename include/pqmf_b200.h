@@ -14,7 +14,9 @@
  *     in _host; the caller owns all buffers (including streaming state);
  *   - functions never allocate device memory, never synchronise, never throw: they enqueue
  *     on `stream` (a cudaStream_t passed as void*) and return 0 on success, a negative
- *     PQMF_ERR_* code for rejected arguments, or a positive cudaError_t value;
+ *     PQMF_ERR_* code for rejected arguments, or a positive cudaError_t value
+ *     (pqmf_roundtrip_host_f32 is the exception: it owns a staging workspace and synchronises);
+ *   - the tensor-core kernels represent every sample by two fp16 terms: |x|, |sub-band| < 65504;
  *   - M = n_band, L = hk.shape[1] (prototype length centre-padded to a power of two,
  *     pqmf.py:26-32), hk is the registered buffer `hk` [M, L] (pqmf.py:230);
  *   - sign mask sigma(k, n) = -1 iff band k is odd and GLOBAL frame index n is even
@@ -37,21 +39,21 @@ extern "C" {
 #define PQMF_ERR_UNSUPPORTED (-2) /* combination the library has no kernel for                    */
 #define PQMF_ERR_NO_DEVICE (-3)   /* no CUDA device / wrong architecture (needs sm_100)          */
 
-/* flags */
-#define PQMF_FLAG_EXACT 1u   /* every term of the registered hk: no fold factorisation, no trimmed correction steps (Hankel kernels with
-                              * trim 0 for large batches, Hankel-16 / register-tiled direct form otherwise) */
-#define PQMF_FLAG_NO_SIGN 2u /* skip sigma(k,n): the reference's free functions polyphase_forward /   *
-                              * classic_* (pqmf.py:115-199) leave reverse_half to the caller; offline only */
-
-#define PQMF_FLAG_NO_PAIR 8u /* n_band 16 offline kernels: one CTA per SM instead of CTA pairs (measurement / debugging)              */
-#define PQMF_FLAG_NO_FOLD 32u /* n_band 16: never use the fold + modulation kernels (a bank that is not window x cosine: the Hankel kernels take hk as it is) */
-#define PQMF_FLAG_FOLD 4u    /* n_band 16 only: force the fold + modulation kernels (the streaming kernels) offline too */
-#define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* from pqmf_build_tables_f32 */
-/* from pqmf_build_tables_f32: edge K-steps (analysis, synthesis) of the offline n_band 16 kernels whose fp16 correction
- * terms are provably below 4e-6 / 9e-6 of max|input| for this bank and are skipped; 0 keeps every term */
+/* flags (OR them; bits 8-23 are produced by pqmf_build_tables_f32 and belong to the tables they were returned with) */
+#define PQMF_FLAG_EXACT 1u    /* every term of the registered hk: no fold factorisation, no trimmed correction steps (Hankel     *
+                               * kernels with trim 0 for large batches / many streams, Hankel-16 or the direct form otherwise)   */
+#define PQMF_FLAG_NO_SIGN 2u  /* skip sigma(k,n): the reference's free functions polyphase_forward / classic_* (pqmf.py:115-199) *
+                               * leave reverse_half to the caller; offline only, runs the register-tiled direct form             */
+#define PQMF_FLAG_FOLD 4u     /* n_band 16: force the fold + modulation kernels (measurement / debugging)                        */
+#define PQMF_FLAG_NO_PAIR 8u  /* n_band 16: launch the Hankel kernels one CTA per SM instead of as CTA pairs (bit-identical)     */
+#define PQMF_FLAG_NO_FOLD 32u /* n_band 16: never use the fold + modulation kernels (a bank that is not window x cosine: the     *
+                               * Hankel kernels take hk as it is)                                                                */
+#define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* first kept tap / 32, kept taps / 32 */
+/* edge K-steps (analysis, synthesis) of the Hankel kernels whose fp16 correction terms are provably below 4e-6 / 9e-6 of
+ * max|input| for this bank and are skipped; 0 keeps every term */
 #define PQMF_FLAG_H4_TRIM(ta, ts) (((unsigned)(ta) << 17) | ((unsigned)(ts) << 20))
-/* from pqmf_build_tables_f32: the bank is too long for one SM's shared memory; the tables hold two tap ranges (TAPS = one of
- * them) that run as two launches, the second accumulating into the output (n_band 64, long prototypes at n_band 32) */
+/* the bank is too long for one SM's shared memory: the tables hold two tap ranges (TAPS describes one of them) that run as two
+ * launches, the second accumulating into the output (n_band 64, long prototypes at n_band 32) */
 #define PQMF_FLAG_H4_SPLIT (1u << 23)
 
 typedef void* pqmf_stream_t; /* cudaStream_t */
@@ -61,7 +63,8 @@ const char* pqmf_strerror(int code);
 
 /* Which kernel family a call with these parameters would use: 0 = register-tiled direct form (generic),
  * 1 = the tensor-core kernels: n_band 16 / L 512 (Hankel-4 offline, fold + modulation for streaming blocks and small
- * batches, Hankel-16 with PQMF_FLAG_EXACT) and n_band 8 / 32 (Hankel offline, large batches).  `tables` may be NULL. */
+ * batches and few streams, Hankel-4 streaming for many streams) and n_band 8 / 32 / 64 (Hankel offline, large batches).
+ * `tables` may be NULL. */
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
 
 /* ---- coefficient tables for the fast path (host side, one-off; replaces nothing in the reference:
