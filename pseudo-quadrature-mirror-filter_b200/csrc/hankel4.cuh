@@ -1,4 +1,5 @@
-// Offline PQMF for n_band 8 / 16 / 32: the direct form as an implicit-Hankel GEMM on the tensor cores, 64 samples per operand row.
+// Offline PQMF for n_band 8 / 16 / 32 / 64: the direct form as an implicit-Hankel GEMM on the tensor cores, 64 samples per operand row.
+// (n_band 64 and other banks too long for one SM's shared memory run as two tap ranges = two launches, the second accumulating.)
 //
 // hankel16.cuh shows that a strided signal can be fed to tcgen05.mma without im2col (one frame = 32 B = the SWIZZLE_32B row
 // pitch), but there every 16 taps cost a full shared-memory read of the 128-row A tile (~111 B/sample: smem-bound at ~30 % of
