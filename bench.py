@@ -321,7 +321,7 @@ def run_gpu(args):
 
 def other_configs(torch, pq, mod, x, n_samples, peak):
     """Burst timing (6 launches per timed interval, best of 5: the board has not reached its power cap yet) of the headline
-    round trip, n_band 8 / 32 / 64 at the same shape, and config 3 (4096 streams x 2048-sample blocks, state carried)."""
+    round trip, n_band 4 / 8 / 32 / 64 at the same shape, and config 3 (4096 streams x 2048-sample blocks, state carried)."""
     def burst(fn, n=5, inner=6):
         for _ in range(2):
             fn()
@@ -347,7 +347,7 @@ def other_configs(torch, pq, mod, x, n_samples, peak):
         out["n_band16_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n_samples / (ta + ts) * 1e-3, 1),
                                  "frac": round(16 * n_samples / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
         del y
-        for m in (8, 32, 64):
+        for m in (4, 8, 32, 64):
             bank = pq.PQMF(100, m).to(x.device)
             ym = bank(x)
             ta, ts = burst(lambda: bank(x), 3, 4), burst(lambda: bank.inverse(ym), 3, 4)

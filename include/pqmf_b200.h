@@ -76,7 +76,7 @@ int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
  * *fast_flags (may be NULL) receives the PQMF_FLAG_TAPS(...) bits describing which taps are pure zero padding and the
  * PQMF_FLAG_H4_TRIM(...) bits; OR them into the `flags` of every compute call that is given these tables (the images are
  * built for exactly those taps: without the TAPS bits the offline Hankel kernels are not used).
- * Supported: n_band 16 / L 512 (all kernel families); n_band 8 / 16 / 32 / 64 with L = 16, 32 or 64 n_band (offline Hankel kernels).
+ * Supported: n_band 16 / L 512 (all kernel families); n_band 4 / 8 / 16 / 32 / 64 with L = 16, 32 or 64 n_band (offline Hankel kernels).
  * Returns PQMF_ERR_UNSUPPORTED (and writes nothing) when (M, L) has no fast path or the bank does not fit one SM. */
 long pqmf_tables_numel(int M, int L);
 int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int M, int L, float* tables_host,

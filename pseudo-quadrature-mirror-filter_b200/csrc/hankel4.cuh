@@ -102,8 +102,9 @@ __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_a
 
 template <int N>
 __device__ __forceinline__ void h4_tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
-  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "columns per load");
-  if constexpr (N == 4) ptx::tmem_ld4(taddr, r);
+  static_assert(N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "columns per load");
+  if constexpr (N == 2) ptx::tmem_ld2(taddr, r);
+  else if constexpr (N == 4) ptx::tmem_ld4(taddr, r);
   else if constexpr (N == 8) ptx::tmem_ld8(taddr, r);
   else if constexpr (N == 16) ptx::tmem_ld16(taddr, r);
   else ptx::tmem_ld32(taddr, r);
@@ -429,7 +430,8 @@ struct H4SynthesisParams {
 template <int M, bool PAIR>
 __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
   constexpr int FR = 64 / M;       // frames per 128-byte plane row ([frame][band] fp16)
-  constexpr int NBG = M / 8;       // band groups of 8 (one 16-byte chunk per frame)
+  constexpr int NBG = M >= 8 ? M / 8 : 1;     // band groups: a 16-byte chunk is 8 bands of one frame, or (n_band 4) all bands of two frames
+  constexpr int FPI = M >= 8 ? 4 : 32 / M;   // frames per load/convert item (four chunks)
   extern __shared__ __align__(1024) unsigned char h4s_smem[];
   const H4Shape g = p.g;
   const H4Smem sm = h4_carve(h4s_smem, g);
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     // ---- workers.  Item (fq, bg): frames 4 fq .. 4 fq + 3 of bands 8 bg .. 8 bg + 7 = eight float4 loads (prefetched one
     //      tile ahead) -> four 16-byte chunks per fp16 plane.  bg-major thread order keeps a quarter-warp on eight consecutive
     //      frame quads of one band group: their SWIZZLE_128B images hit eight different bank groups at n_band 8 and 16.
-    const int n_fq = (g.rows * FR + 3) / 4;                  // frame quads per plane (the last one may run into the plane's padding)
+    const int n_fq = (g.rows * FR + FPI - 1) / FPI;          // items per band group (the last one may run into the plane's padding)
     const int bg = tid / n_fq, fq = tid - bg * n_fq;
     const bool has_item = tid < n_fq * NBG;
     float4 v0[8];  // prefetched one tile ahead
@@ -467,32 +469,55 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         bb = n_rows - 1 - bb;
         cc = tpr - 1 - cc;
       }
-      const long n = (long)cc * (kH4Rows * FR) + nbase + 4 * fq;
-      const float* sp = p.s + ((size_t)bb * M + 8 * bg) * p.F + n;
-      const bool ok = bb < n_rows && has_item && n >= 0 && n + 3 < p.F;
+      const long n = (long)cc * (kH4Rows * FR) + nbase + FPI * fq;
+      const bool live = bb < n_rows && has_item;
+      if constexpr (M >= 8) {  // v[kk] = frames n .. n + 3 of band 8 bg + kk
+        const float* sp = p.s + ((size_t)bb * M + 8 * bg) * p.F + n;
+        const bool ok = live && n >= 0 && n + 3 < p.F;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {                 // n_band 4: v[2 b + h] = frames n + 4 h .. n + 4 h + 3 of band b
+        const float* sp = p.s + (size_t)bb * M * p.F + n;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int b4 = kk >> 1, h = kk & 1;
+          const bool ok = live && n + 4 * h >= 0 && n + 4 * h + 3 < p.F;
+          v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)b4 * p.F + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     };
     // sigma(k, n): odd bands (odd kk) flip on even global frames; quads start on multiples of 4, so the parity is j's
     const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
     auto convert = [&](const float4 (&v)[8], int pb) {
       if (!has_item) return;
       unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
+      auto comp = [](const float4& q, int c) { return c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w; };
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t fl = (j & 1) ? flip_odd : flip_even;
         float w[8];
+        uint32_t o;
+        if constexpr (M >= 8) {  // chunk j = frame 4 fq + j, bands 8 bg .. 8 bg + 7
+          const uint32_t fl = (j & 1) ? flip_odd : flip_even;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const float t = j == 0 ? v[kk].x : j == 1 ? v[kk].y : j == 2 ? v[kk].z : v[kk].w;
-          w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
+          for (int kk = 0; kk < 8; ++kk) {
+            const float t = comp(v[kk], j);
+            w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
+          }
+          o = sw128_offset((uint32_t)(4 * fq + j) * (2u * M) + 16u * bg);
+        } else {                 // n_band 4: chunk j = frames 8 fq + 2 j (even) and + 1 (odd), four bands each
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int b4 = kk & 3, odd = kk >> 2;
+            const float t = comp(v[2 * b4 + (j >> 1)], 2 * (j & 1) + odd);
+            w[kk] = (b4 & 1) ? __uint_as_float(__float_as_uint(t) ^ (odd ? flip_odd : flip_even)) : t;
+          }
+          o = sw128_offset((uint32_t)(8 * fq + 2 * j) * (2u * M));
         }
         uint4 h1, h2;
         split2_f16(w[0], w[1], h1.x, h2.x);
         split2_f16(w[2], w[3], h1.y, h2.y);
         split2_f16(w[4], w[5], h1.z, h2.z);
         split2_f16(w[6], w[7], h1.w, h2.w);
-        const uint32_t o = sw128_offset((uint32_t)(4 * fq + j) * (2u * M) + 16u * bg);  // frame 4 fq + j, bands 8 bg .. 8 bg + 7
         *reinterpret_cast<uint4*>(p1 + o) = h1;
         *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
       }
@@ -686,13 +711,13 @@ inline void hankel4_build_banks(const float* hk /*[M][L]*/, int M, int L, int jl
         const size_t at = ((size_t)kc * 128 + row) * 8 + e8;
         {  // analysis: K index = tap offset within the (delta-shifted) window, q = band
           const int j = kap - M * delta;
-          const float v = (j >= 0 && j < kt) ? sa * hk[(size_t)q * L + jlo + j] : 0.f;
+          const float v = (j >= 0 && j < kt && jlo + j < L) ? sa * hk[(size_t)q * L + jlo + j] : 0.f;
           const float c1 = __half2float(__float2half_rn(v));
           img_analysis[at] = part == 0 ? bits(c1) : bits(v - c1);
         }
         {  // synthesis: K index = (frame e, band kb) of the [frame][band] plane: lag = delta + ehi - e, tap M lag + q, q = output phase
           const int e = kap / M, kb = kap % M, lag = delta + ehi - e;
-          const float v = (lag >= elo && lag <= ehi) ? ss * hk[(size_t)kb * L + M * lag + q] : 0.f;
+          const float v = (lag >= elo && lag <= ehi && M * lag + q < L) ? ss * hk[(size_t)kb * L + M * lag + q] : 0.f;
           const float c1 = __half2float(__float2half_rn(v));
           img_synthesis[at] = part == 0 ? bits(c1) : bits(v - c1);
         }
@@ -728,10 +753,10 @@ inline int hankel4_pick_trim(const float* hk /*[M][L]*/, int M, int L, int jlo, 
               const int kap = 16 * s + e16;
               if (!synthesis) {
                 const int j = kap - M * delta;
-                if (j >= 0 && j < kt) sum += fabs((double)hk[(size_t)q * L + jlo + j]);
+                if (j >= 0 && j < kt && jlo + j < L) sum += fabs((double)hk[(size_t)q * L + jlo + j]);
               } else {
                 const int e = kap / M, kb = kap % M, lag = delta + ehi - e;
-                if (lag >= elo && lag <= ehi) sum += (double)M * fabs((double)hk[(size_t)kb * L + M * lag + q]);
+                if (lag >= elo && lag <= ehi && M * lag + q < L) sum += (double)M * fabs((double)hk[(size_t)kb * L + M * lag + q]);
               }
             }
           }

@@ -144,16 +144,19 @@ constexpr long kH4PairImageFloats = 2L * 35 * 3072 / 4;  // per-rank images of t
 
 // ---- offline default for n_band 8 / 16 / 32 / 64: the 64-samples-per-row Hankel GEMM (hankel4.cuh) when there are enough tiles ----
 // prototype lengths: L = 32 M at attenuation ~100, 16 M / 64 M for shorter / longer designs
-bool h4_family(int M, int L) { return (M == 8 || M == 16 || M == 32 || M == 64) && (L == 16 * M || L == 32 * M || L == 64 * M); }
+bool h4_family(int M, int L) { return (M == 4 || M == 8 || M == 16 || M == 32 || M == 64) && (L == 16 * M || L == 32 * M || L == 64 * M); }
 int h4_ks(int M, int kt) { return (kt + 64 - M + 15) / 16; }
 // one CTA-pair image = [2 ranks][2 ks][96 rows][8] fp16 = 1536 ks floats.  Region sizes are fixed by (M, L) alone: a bank that
 // fits one SM uses [analysis | synthesis], sized for kt = L; a longer one is SPLIT into two tap ranges that run as two launches
 // (the second accumulates): [analysis lo | analysis hi | synthesis lo | synthesis hi], each sized for kt = L / 2.
-long h4_pair_floats(int M, int L) { return 1536L * h4_ks(M, L); }
+// n_band 4: a frame is 8 bytes, but operand windows start on 16-byte boundaries, so the synthesis alignment pad must be an even
+// number of frames; the tables therefore hold TWO synthesis images (largest lag ehi and ehi + 1) and the launch picks the one
+// that makes (o - ehi) even.  Image regions are sized for that one extra frame of lag.
+long h4_pair_floats(int M, int L) { return 1536L * h4_ks(M, L + (M < 8 ? M : 0)); }
 long h4_half_floats(int M, int L) { return 1536L * h4_ks(M, L / 2); }
 long h4_pair_offset(int M, int L) { return pqmf::hankel16_supported(M, L) ? kH4PairOffset : 0; }  // those tables start with the fold / Hankel-16 parts
 long h4_tables_floats(int M, int L) {
-  const long whole = 2 * h4_pair_floats(M, L), split = 4 * h4_half_floats(M, L);
+  const long whole = (M < 8 ? 3 : 2) * h4_pair_floats(M, L), split = 4 * h4_half_floats(M, L);
   return whole > split ? whole : split;
 }
 bool use_h4(int B, long F, int M, const float* hist) {
@@ -210,6 +213,7 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   pqmf::H4AnalysisParams p{};
   p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.keep_in_l2 = 1;
   switch (M) {
+    case 4: return h4_analysis_m<4>(p, tables, jlo, kt, B, L, flags, st);
     case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, L, flags, st);
     case 16: return h4_analysis_m<16>(p, tables, jlo, kt, B, L, flags, st);
     case 32: return h4_analysis_m<32>(p, tables, jlo, kt, B, L, flags, st);
@@ -235,8 +239,12 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
   }
   p.trim_lo = p.trim_hi = trim;
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
-    p.g = pqmf::h4_shape(M, jlo, kt, true, true);
-    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + h4_pair_floats(M, L));
+    // n_band 4: the image whose largest lag makes (o - ehi) even (see h4_pair_floats); its K-steps sit one frame later, so give
+    // up one trimmed step to stay inside the error budget that was computed for the other image
+    const int variant = (M < 8) ? ((p.o - ((jlo + kt) / M - 1)) & 1) : 0;
+    if (variant) p.trim_lo = p.trim_hi = trim > 0 ? trim - 1 : 0;
+    p.g = pqmf::h4_shape(M, jlo, kt + variant * M, true, true);
+    p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + (1 + variant) * h4_pair_floats(M, L));
     const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st);
     if (e == 0) return 0;
     (void)cudaGetLastError();
@@ -257,6 +265,7 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
   pqmf::H4SynthesisParams p{};
   p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0; p.reverse = 1;
   switch (M) {
+    case 4: return h4_synthesis_m<4>(p, tables, jlo, kt, B, L, flags, st);
     case 8: return h4_synthesis_m<8>(p, tables, jlo, kt, B, L, flags, st);
     case 16: return h4_synthesis_m<16>(p, tables, jlo, kt, B, L, flags, st);
     case 32: return h4_synthesis_m<32>(p, tables, jlo, kt, B, L, flags, st);
@@ -436,6 +445,12 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
       pqmf::hankel4_build_banks(hk_host, M, L, jlo, kt, ia.data(), is.data());
       pqmf::hankel4_pair_image(ia.data(), ks, base);
       pqmf::hankel4_pair_image(is.data(), ks, base + 2 * h4_pair_floats(M, L));
+      if (M < 8) {  // the synthesis image with one more (all-zero) lag at the top, see h4_pair_floats
+        const int ks1 = h4_ks(M, kt + M);
+        std::vector<uint16_t> ia1((size_t)2 * ks1 * 128 * 8), is1((size_t)2 * ks1 * 128 * 8);
+        pqmf::hankel4_build_banks(hk_host, M, L, jlo, kt + M, ia1.data(), is1.data());
+        pqmf::hankel4_pair_image(is1.data(), ks1, base + 2 * (2 * h4_pair_floats(M, L)));
+      }
     } else {
       for (int half = 0; half < 2; ++half) {
         pqmf::hankel4_build_banks(hk_host, M, L, jlo + half * kt, kt, ia.data(), is.data());

@@ -335,9 +335,10 @@ def test_hankel4_full_length_bank(golden, pq):
 
 
 # ------------------------------------------------------------------ n_band 8 / 32 on the 64-samples-per-row Hankel kernels
-@pytest.mark.parametrize("m,b,frames", ((8, 24, 4096), (8, 50, 2100), (32, 24, 1024), (32, 49, 516), (8, 3, 8192 * 5 + 4)))
+@pytest.mark.parametrize("m,b,frames", ((8, 24, 4096), (8, 50, 2100), (32, 24, 1024), (32, 49, 516), (8, 3, 8192 * 5 + 4), (4, 24, 8192), (4, 33, 6148),
+                                         (4, 5, 2048 * 21 + 12)))
 def test_hankel_other_band_counts_vs_oracle(golden, pq, m, b, frames):
-    """>= 96 tiles of 8192 samples: the dispatcher picks hankel4.cuh for n_band 8 and 32 too (same MMA shapes, N = 128)."""
+    """>= 96 tiles of 8192 samples: the dispatcher picks hankel4.cuh for n_band 4, 8 and 32 too (same MMA shapes, N = 128)."""
     hk = golden(f"bank_M{m}.npz")["hk"]
     t = m * frames
     x = O.audio_like((b, 1, t), 7 * m + frames)
@@ -358,7 +359,7 @@ def test_hankel_other_band_counts_vs_oracle(golden, pq, m, b, frames):
     assert np.abs(oc[:, 0] - O.synthesis(s, hk, delay_frames=1)).max() <= TOL / 2
 
 
-@pytest.mark.parametrize("att,m", ((60, 16), (140, 16), (60, 32), (140, 8), (60, 8), (80, 16), (100, 64), (120, 32), (60, 64)))
+@pytest.mark.parametrize("att,m", ((60, 16), (140, 16), (60, 32), (140, 8), (60, 8), (80, 16), (100, 64), (120, 32), (60, 64), (80, 4), (120, 4)))
 def test_hankel_other_prototype_lengths(pq, att, m):
     """Prototype lengths other than 32 n_band (L = 16 M or 64 M): tap span, K-steps and trims come from the actual bank.  Banks too
     long for one SM's shared memory (n_band 64; attenuation 120 at n_band 32) run as two tap ranges, the second launch accumulating."""

@@ -165,11 +165,11 @@ def test_tables_exist_for_the_tensor_core_band_counts_and_degrade_gracefully():
     import pqmf_b200 as pq
 
     assert (pq.PQMF(100, 64)._flags >> 23) & 1 and (pq.PQMF(120, 32)._flags >> 23) & 1  # split into two tap ranges
-    for m, jlo, kt in ((8, 32, 192), (16, 64, 384), (32, 128, 768)):
+    for m, jlo, kt in ((4, 0, 128), (8, 32, 192), (16, 64, 384), (32, 128, 768)):
         mod = pq.PQMF(100, m)
         assert mod._tables.numel() > 0
         assert 32 * ((mod._flags >> 8) & 15) == jlo and 32 * ((mod._flags >> 12) & 31) == kt
         assert 0 < ((mod._flags >> 17) & 7) <= 7 and 0 < ((mod._flags >> 20) & 7) <= 7
-    for att, m in ((120, 64), (100, 4), (100, 2)):
+    for att, m in ((120, 64), (100, 2)):
         mod = pq.PQMF(att, m)
         assert mod._tables.numel() == 0 and (mod._flags >> 8) == 0

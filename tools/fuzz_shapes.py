@@ -8,7 +8,7 @@ random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 empty = torch.zeros(0, device="cuda")
 worst = {}
 for case in range(int(sys.argv[2]) if len(sys.argv) > 2 else 60):
-    m = random.choice((8, 16, 16, 32, 64))
+    m = random.choice((4, 8, 16, 16, 32, 64))
     att = random.choice((80, 100, 100, 120))
     try:
         mod = pq.CachedPQMF(att, m).cuda()
