@@ -150,15 +150,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    batch = 8  # bounded sample of the workload: 8 of the 64 rows per step (~0.25 s of host work per step)
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
-    steps = min(steps, 20)
+    # the SAME workload as the GPU arm: all 64 rows of 2^20 samples per step (~0.3 s of host work per step on the GPU box's 16
+    # threads), the same warm-up count; the step count is bounded so that the run ends within a few minutes on any host
+    batch = BATCH
+    steps, warmup = max(1, min(args.steps, 30)), max(1, min(args.warmup, 5))
     val, threads, f, i = cpu_port_throughput(batch, N_SAMPLES, repeats=steps, warmup=warmup)
-    sample = f"{batch} x 2^20 samples per step (1/8 of the 64-row batch), best of {steps} steps after {warmup} warm-up; torch-CPU port of pqmf.py:115-157"
+    sample = (f"{batch} x 2^20 samples per step (the whole configs[1] batch), best of {steps} steps after {warmup} warm-up; torch-CPU port of "
+              f"pqmf.py:115-157 on {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": round((f + i) * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "n_band": N_BAND, "timing": "host wall clock (time.perf_counter)"},
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_band": N_BAND, "batch_per_gpu": BATCH, "samples_per_row": N_SAMPLES,
+                   "timing": "host wall clock (time.perf_counter)"},
         "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -266,31 +270,33 @@ def run_gpu(args):
         e2e_ms = float(t.item())
     e2e_value = n_gpus * BATCH * N_SAMPLES / (e2e_ms * 1e-3) * 1e-6
     _lib.cabi.pqmf_host_release()
+    del hx, ho
+
+    peak, peak_src = measured_peak_gbs()
+    other = None if args.no_other_configs else other_configs(torch, dist, pq, dev, mod, x, peak, n_gpus, distributed)
 
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak_gbs()
     algo_bytes = ALGO_BYTES_PER_SAMPLE_PER_DIRECTION * BATCH * N_SAMPLES
     kernels = {
         "h4_analysis_kernel": {"ms": t_an, "gbs": algo_bytes / (t_an * 1e-3) * 1e-9},
         "h4_synthesis_kernel": {"ms": t_sy, "gbs": algo_bytes / (t_sy * 1e-3) * 1e-9},
     }
     dominant = max(kernels, key=lambda k: kernels[k]["ms"])
-    traffic = recorded_traffic().get(dominant)
+    traffic = recorded_traffic().get(dominant)  # NOT measured in this run: ncu counters cannot be read while timing
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": round(kernels[dominant]["gbs"], 1), "peak": peak, "unit": "GB/s",
-        "frac": round(kernels[dominant]["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+        "frac": round(kernels[dominant]["gbs"] / peak, 4), "traffic": traffic,
+        "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the committed ncu --set full capture",
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes,
         "per_kernel": {k: {"ms": round(v["ms"], 4), "achieved_gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4)} for k, v in kernels.items()},
         "round_trip_frac": round(2 * algo_bytes / ((t_an + t_sy) * 1e-3) * 1e-9 / peak, 4),
     }
     # ---- informational: the same kernels outside the power-capped steady state, and the other BASELINE configs (not the metric)
-    other = None
-    if n_gpus == 1:
-        other = other_configs(torch, pq, mod, x, BATCH * N_SAMPLES, peak)
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         cb, cr = 8, 5
@@ -319,50 +325,136 @@ def run_gpu(args):
     return 0
 
 
-def other_configs(torch, pq, mod, x, n_samples, peak):
-    """Burst timing (6 launches per timed interval, best of 5: the board has not reached its power cap yet) of the headline
-    round trip, n_band 4 / 8 / 32 / 64 at the same shape, and config 3 (4096 streams x 2048-sample blocks, state carried)."""
-    def burst(fn, n=5, inner=6):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        best = float("inf")
-        for _ in range(n):
-            fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(inner):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1) / inner)
-        return best
+def _max_over_ranks(torch, dist, dev, ms: float, distributed: bool) -> float:
+    if not distributed:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
-    out = {"note": "informational, burst-timed (not the metric): Msamples/s and fraction of the HBM roofline (16 B/sample round trip)"}
+
+def _sustained(torch, fn, seconds: float, min_steps: int = 10, max_steps: int = 2000):
+    """ms per call of `fn` over a back-to-back run of about `seconds` (CUDA events on the current stream; the step count is fixed
+    from a short calibration so that every rank times the same number of steps)."""
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
-    time.sleep(1.0)  # let the board leave the power-capped state of the main loop
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1) / 3, 1e-3)
+    steps = int(min(max_steps, max(min_steps, seconds * 1e3 / est)))
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, steps
+
+
+def _burst(torch, fn, n=5, inner=6):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(n):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / inner)
+    return best
+
+
+def bench_config3(torch, pq, dev, seconds):
+    """configs[2]: 4096 concurrent streams x block 2048, state carried across blocks (CachedPQMF streaming mode), per GPU.
+    One step = forward_stream + inverse_stream of one block of every stream.  Algorithmic bytes: 16 B/sample + the 8192 B of
+    state traffic per stream-block of the explicit-state formulation = 20 B/sample."""
+    streams, block = 4096, 2048
+    gen = torch.Generator(device=dev).manual_seed(33)
+    xs = (0.5 * torch.randn(streams, 1, block, device=dev, generator=gen)).clamp_(-1, 1)
+    cached = pq.CachedPQMF(ATTEN, N_BAND).to(dev)
+
+    def step():
+        cached.inverse_stream(cached.forward_stream(xs))
+
+    ms, steps = _sustained(torch, step, seconds, min_steps=64)
+    return {"workload": "configs[2]: 4096 streams x block 2048 per GPU, state carried", "samples_per_step": streams * block, "steps": steps, "ms": ms,
+            "bytes_per_sample": 20}
+
+
+def bench_config4(torch, pq, dev, seconds):
+    """configs[3]: n_band 4 / 8 / 32 / 64 on 8-channel 48 kHz 60 s clips folded into the batch (8 clips -> 64 rows x 2 880 000), per GPU."""
+    rows, t = 64, 2_880_000
+    gen = torch.Generator(device=dev).manual_seed(44)
+    x = (0.5 * torch.randn(rows, 1, t, device=dev, generator=gen)).clamp_(-1, 1)
+    out = {}
+    for m in (4, 8, 32, 64):
+        bank = pq.PQMF(ATTEN, m).to(dev)
+        y = bank(x)
+        ta, _ = _sustained(torch, lambda: bank(x), seconds / 8, min_steps=5)
+        ts, _ = _sustained(torch, lambda: bank.inverse(y), seconds / 8, min_steps=5)
+        out[m] = (ta, ts)
+        del y, bank
+    return {"workload": "configs[3]: 8 clips x 8 ch x 60 s @ 48 kHz folded to 64 rows x 2 880 000 per GPU, n_band 4/8/32/64 (polyphase; classic runs the same kernel)",
+            "samples_per_step": rows * t, "per_band_ms": out, "bytes_per_sample": 16}
+
+
+def bench_config5(torch, pq, dev, seconds):
+    """configs[4]: one GPU's shard of 8192 stereo clips x 10 s @ 48 kHz = 2048 rows x 480 000, CachedPQMF.forward + .inverse."""
+    rows, t = 2048, 480_000
+    x = torch.empty(rows, 1, t, device=dev)
+    x.normal_(0, 0.5).clamp_(-1, 1)
+    mod = pq.CachedPQMF(ATTEN, N_BAND).to(dev)
+    holder = {}
+
+    def step():
+        holder["y"] = mod(x)
+        holder["o"] = mod.inverse(holder["y"])
+
+    ms, steps = _sustained(torch, step, seconds, min_steps=5, max_steps=200)
+    return {"workload": "configs[4]: 2048 rows x 480 000 samples per GPU (8192 stereo clips x 10 s @ 48 kHz over 8 GPUs), CachedPQMF forward+inverse",
+            "samples_per_step": rows * t, "steps": steps, "ms": ms, "bytes_per_sample": 16}
+
+
+def other_configs(torch, dist, pq, dev, mod, x, peak, n_gpus, distributed):
+    """The other BASELINE.json configs, SUSTAINED (each timed back to back for ~0.5 s) and at every N (each rank runs its own shard,
+    the time is the max over ranks): Msamples/s whole-job and fraction of the per-GPU HBM roofline.  Plus the burst figure of the headline
+    kernels (6 launches per interval, before the board reaches its power cap) for reference."""
+    out = {"note": "sustained unless marked burst; Msamples/s are whole-job (all GPUs); frac = algorithmic bytes / time / (n_gpus x measured HBM peak)"}
+
+    def entry(res):
+        ms = _max_over_ranks(torch, dist, dev, res["ms"], distributed)
+        val = n_gpus * res["samples_per_step"] / ms * 1e-3
+        return {"workload": res["workload"], "steps": res.get("steps"), "ms_per_step": round(ms, 4), "value": round(val, 1), "unit": UNIT,
+                "frac": round(res["bytes_per_sample"] * res["samples_per_step"] / (ms * 1e-3) * 1e-9 / peak, 4), "bytes_per_sample": res["bytes_per_sample"]}
+
+    torch.cuda.synchronize()
     try:
-        y = mod(x)
-        ta, ts = burst(lambda: mod(x)), burst(lambda: mod.inverse(y))
-        out["n_band16_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n_samples / (ta + ts) * 1e-3, 1),
-                                 "frac": round(16 * n_samples / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
-        del y
-        for m in (4, 8, 32, 64):
-            bank = pq.PQMF(100, m).to(x.device)
-            ym = bank(x)
-            ta, ts = burst(lambda: bank(x), 3, 4), burst(lambda: bank.inverse(ym), 3, 4)
-            out[f"n_band{m}_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n_samples / (ta + ts) * 1e-3, 1),
-                                       "frac": round(16 * n_samples / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
-            del ym, bank
-        cached = pq.CachedPQMF(100, 16).to(x.device)
-        xs = x.reshape(-1)[: 4096 * 2048].reshape(4096, 1, 2048).contiguous()
-
-        def step():
-            cached.inverse_stream(cached.forward_stream(xs))
-
-        tb = burst(step, 5, 20)
-        out["config3_streaming"] = {"streams": 4096, "block": 2048, "ms_per_block_step": round(tb, 4), "round_trip": round(4096 * 2048 / tb * 1e-3, 1),
-                                    "frac_of_20B_per_sample_roofline": round(20 * 4096 * 2048 / (tb * 1e-3) * 1e-9 / peak, 4)}
+        if n_gpus == 1:
+            time.sleep(1.0)  # let the board leave the power-capped state of the main loop
+            n = x.numel()
+            y = mod(x)
+            ta, ts = _burst(torch, lambda: mod(x)), _burst(torch, lambda: mod.inverse(y))
+            out["n_band16_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n / (ta + ts) * 1e-3, 1),
+                                     "frac": round(16 * n / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
+            del y
+        out["config3"] = entry(bench_config3(torch, pq, dev, 0.5))
+        r4 = bench_config4(torch, pq, dev, 2.0)
+        per = {}
+        for m, (ta, ts) in r4["per_band_ms"].items():
+            ta = _max_over_ranks(torch, dist, dev, ta, distributed)
+            ts = _max_over_ranks(torch, dist, dev, ts, distributed)
+            per[f"n_band{m}"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "value": round(n_gpus * r4["samples_per_step"] / (ta + ts) * 1e-3, 1),
+                                 "unit": UNIT, "frac": round(16 * r4["samples_per_step"] / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
+        out["config4"] = {"workload": r4["workload"], "per_band": per}
+        out["config5"] = entry(bench_config5(torch, pq, dev, 0.5))
     except Exception as exc:  # never let the informational part break the contract line
         out["error"] = repr(exc)
     return out
@@ -375,6 +467,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the sustained runs of configs 3 / 4 / 5 that are appended to the line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -385,7 +478,8 @@ def main():
 
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps",
-               str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
+                   ["--no-other-configs"] if args.no_other_configs else [])
         return subprocess.call(cmd)
     return run_gpu(args)
 

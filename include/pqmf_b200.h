@@ -40,16 +40,22 @@ extern "C" {
 #define PQMF_ERR_NO_DEVICE (-3)   /* no CUDA device / wrong architecture (needs sm_100)          */
 
 /* flags (OR them; bits 8-23 are produced by pqmf_build_tables_f32 and belong to the tables they were returned with) */
-#define PQMF_FLAG_EXACT 1u    /* every term of the registered hk: no fold factorisation, no trimmed correction steps (Hankel     *
-                               * kernels with trim 0 for large batches / many streams, Hankel-16 or the direct form otherwise)   */
+#define PQMF_FLAG_EXACT 1u    /* every term of the registered hk: no fold factorisation, no trimmed correction steps.  Still the  *
+                               * TENSOR-CORE kernels wherever they exist (Hankel kernels with trim 0 for large batches / many      *
+                               * streams, Hankel-16 for small n_band 16 calls; the direct form elsewhere), i.e. samples are still  *
+                               * carried as two fp16 terms (|x| < 65504).  PQMF_FLAG_FP32 is the plain-fp32 path.                  */
 #define PQMF_FLAG_NO_SIGN 2u  /* skip sigma(k,n): the reference's free functions polyphase_forward / classic_* (pqmf.py:115-199) *
                                * leave reverse_half to the caller; offline only, runs the register-tiled direct form             */
 #define PQMF_FLAG_FOLD 4u     /* n_band 16: force the fold + modulation kernels (measurement / debugging)                        */
+#define PQMF_FLAG_FP32 16u    /* plain fp32 arithmetic on the CUDA cores (register-tiled direct form) for every shape: no fp16-pair   *
+                               * representation of the samples, hence no range limit and fp32's relative accuracy at any signal     *
+                               * level -- the arithmetic of the reference's conv1d, ~20x slower than the tensor-core kernels        */
 #define PQMF_FLAG_NO_PAIR 8u  /* n_band 16: launch the Hankel kernels one CTA per SM instead of as CTA pairs (bit-identical)     */
+#define PQMF_FLAG_NO_PREFETCH 64u /* offline Hankel kernels: no L2 prefetch of the tile after next (bit-identical; measurement)        */
 #define PQMF_FLAG_NO_FOLD 32u /* n_band 16: never use the fold + modulation kernels (a bank that is not window x cosine: the     *
                                * Hankel kernels take hk as it is)                                                                */
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* first kept tap / 32, kept taps / 32 */
-/* edge K-steps (analysis, synthesis) of the Hankel kernels whose fp16 correction terms are provably below 4e-6 / 9e-6 of
+/* edge K-steps (analysis, synthesis) of the Hankel kernels whose fp16 correction terms are provably below 6e-6 / 1.5e-5 of
  * max|input| for this bank and are skipped; 0 keeps every term */
 #define PQMF_FLAG_H4_TRIM(ta, ts) (((unsigned)(ta) << 17) | ((unsigned)(ts) << 20))
 /* the bank is too long for one SM's shared memory: the tables hold two tap ranges (TAPS describes one of them) that run as two

@@ -23,7 +23,9 @@ PQMF_FLAG_EXACT = 1
 PQMF_FLAG_NO_SIGN = 2
 PQMF_FLAG_FOLD = 4
 PQMF_FLAG_NO_PAIR = 8
+PQMF_FLAG_FP32 = 16
 PQMF_FLAG_NO_FOLD = 32
+PQMF_FLAG_NO_PREFETCH = 64
 PQMF_FLAG_H4_SPLIT = 1 << 23
 
 

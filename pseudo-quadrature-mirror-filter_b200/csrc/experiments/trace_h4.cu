@@ -9,8 +9,8 @@ int main(int argc, char** argv) {
   const bool pair = argc > 4 && atoi(argv[4]) != 0;
   const int B = 64; const long T = 1 << 20, F = T / 16;
   float *x, *y; uint16_t* bank; long long* tr;
-  cudaMalloc(&x, (size_t)B * T * 4); cudaMalloc(&y, (size_t)B * T * 4); cudaMalloc(&bank, 27 * 4096); cudaMalloc(&tr, (64 * 64 + 512) * 8);
-  cudaMemset(x, 0, (size_t)B * T * 4); cudaMemset(bank, 0, 27 * 4096); cudaMemset(tr, 0, 64 * 64 * 8);
+  cudaMalloc(&x, (size_t)B * T * 4); cudaMalloc(&y, (size_t)B * T * 4); cudaMalloc(&bank, 2 * 27 * 4096); cudaMalloc(&tr, (64 * 64 + 512) * 8);
+  cudaMemset(x, 0, (size_t)B * T * 4); cudaMemset(bank, 0, 2 * 27 * 4096); cudaMemset(tr, 0, 64 * 64 * 8);
   if (argc > 1) {   // random signal and bank instead of zeros (does the data change the timing?)
     std::vector<float> hx(1 << 22), hk(16 * 512);
     srand(3);
@@ -23,15 +23,15 @@ int main(int argc, char** argv) {
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   H4AnalysisParams p{};
-  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim_lo = p.trim_hi = argc > 3 ? atoi(argv[3]) : 0; p.g = h4_shape(16, 64, 384, pair, false);
+  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim_lo = p.trim_hi = argc > 3 ? atoi(argv[3]) : 0; p.g = (argc > 6 && atoi(argv[6]) == 2) ? h4_shape(16, 64, 384, pair, false) : h4_shape_deep(16, 64, 384, pair, false); p.no_l2_prefetch = argc > 5 && atoi(argv[5]);
   for (int rep = 0; rep < 3; ++rep) {
     int rc = (pair ? h4_launch_analysis<16, true>(p, B, 0) : h4_launch_analysis<16, false>(p, B, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
   }
-  const bool synth = argc > 2;
+  const bool synth = argc > 2 && argv[2][0] == 's';   // trace_h4 <random> <a|s> <trim> <pair> <no_l2_prefetch> <nbuf 2|3>
   H4SynthesisParams q{};
-  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim_lo = q.trim_hi = argc > 3 ? atoi(argv[3]) : 0; q.g = h4_shape(16, 64, 384, pair, true);
+  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim_lo = q.trim_hi = argc > 3 ? atoi(argv[3]) : 0; q.g = (argc > 6 && atoi(argv[6]) == 2) ? h4_shape(16, 64, 384, pair, true) : h4_shape_deep(16, 64, 384, pair, true); q.no_l2_prefetch = argc > 5 && atoi(argv[5]);
   if (synth) {
     cudaMemset(tr, 0, 64 * 64 * 8);
     (pair ? h4_launch_synthesis<16, true>(q, B, 0) : h4_launch_synthesis<16, false>(q, B, 0));
@@ -56,13 +56,13 @@ int main(int argc, char** argv) {
   }
   const long long t00 = h[(0 * 8 + 1) * 8 + 0];
   printf("warp 1 (MMA warp) and warp 5; cycles relative to the first stamp\n");
-  printf("it |  start   conv   loads  mma_issued  mma(it-1)_done  epi_done | period\n");
+  printf("it |  start   conv   loads+publish  wait+drain(it-lag) | period\n");
   long long prev = t00;
   for (int it = 0; it < 56; ++it) {
     for (int w : {1, 5}) {
       long long* r = &h[((size_t)it * 8 + w) * 8];
       if (!r[0]) continue;
-      printf("%2d w%d %8lld %6lld %6lld %6lld %10lld %10lld", it, w, r[0] - t00, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] ? r[4] - r[3] : 0, r[4] ? r[5] - r[4] : 0);
+      printf("%2d w%d %8lld %6lld %6lld %10lld", it, w, r[0] - t00, r[1] - r[0], r[2] - r[1], r[5] - r[2]);
       if (w == 1) { printf(" | %lld", r[0] - prev); prev = r[0]; }
       printf("\n");
     }

@@ -15,12 +15,23 @@
 // Roles: worker warps convert fp32 -> 2 x fp16 planes (swizzled STS) and drain TMEM; ONE warp only issues the MMAs
 // (tcgen05.mma issue blocks the issuing thread while the tensor queue is full).  With PAIR the kernel runs as clusters of two
 // CTAs sharing the bank operand (cta_group::2).  DESIGN.md section 5 has the measurements behind each of these choices.
+//
+// Round 2: (a) The second fp16 term of every sample and the second term of the bank are scaled by 2^11 (h2' = 2^11 (x - h1),
+// c2' = 2^11 (2^10 hk - c1)) and accumulate in their own TMEM columns: D[:, 0:64] = h1 c1, D[:, 64:128] = h1 c2' + h2' c1, result =
+// 2^-10 (D0 + 2^-11 D1).  Same MMA count, but the residuals stay in the fp16 normal range: the absolute error floor drops from 2^-25 to
+// 2^-36 per sample.  (b) One thread asks the L2 for the input of tile it + 2 (cp.async.bulk.prefetch.L2) while the workers prefetch
+// tile it + 1 into registers: the per-tile timeline (experiments/trace_h4.cu) showed the tensor pipe busy 2380 of ~2890 cycles per
+// tile, the rest lost to DRAM-latency spikes that a one-tile register prefetch cannot absorb.  (Staging the fp32 input in a shared-
+// memory ring by bulk copies instead -- deeper, no registers -- was built and measured: bit-identical and 7-9 % SLOWER, because shared-
+// memory bandwidth is the binding resource here: the tensor pipe already reads ~250 KB of operands per tile, and the ring adds 69 KB.)
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "hankel16.cuh"
 #include "ptx.cuh"
@@ -34,6 +45,7 @@ constexpr int kH4SynThreads = kH4SynWorkers + 32;
 constexpr int kH4Rows = 128;                    // A rows per tile
 constexpr int kH4TileSamples = 64 * kH4Rows;    // 8192 samples (= 128 FR frames) per tile
 constexpr int kH4MaxPlaneRows = 144;            // register prefetch / item counts are sized for this: K-steps <= 64
+constexpr float kH4Res = 2048.0f;               // scale of the second fp16 term of samples and bank (2^11)
 
 // K-major SWIZZLE_128B descriptor: rows 128 B apart, 8-row groups 1024 B apart, 16-byte chunk index ^= address bits 7-9
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -56,9 +68,10 @@ struct H4Shape {
   int jlo, kt, ks;     // first non-zero tap, taps kept (multiples of 32), K-steps = ceil((kt + 64 - M) / 16)
   int rows, plane;     // 128-byte rows of one fp16 plane, bytes per plane (multiple of 1024)
   int bank;            // bytes of one CTA's bank image: [2 ks chunks][96 or 128 rows][16 B]
+  int nbuf;            // plane pairs in shared memory = accumulators in TMEM (2 or 3): how far the workers may run ahead of the tensor pipe
   int bytes;           // dynamic shared memory
 };
-inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
+inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis, int nbuf = 2) {
   H4Shape g;
   g.jlo = jlo;
   g.kt = kt;
@@ -67,14 +80,22 @@ inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
   g.rows = kH4Rows + (32 * g.ks + pad_bytes - 1) / 128;
   g.plane = ((g.rows * 128 + 1023) / 1024) * 1024;
   g.bank = g.ks * 2 * (pair ? 96 : 128) * 16;
-  g.bytes = g.bank + 4 * g.plane + 128;
+  g.nbuf = nbuf;
+  g.bytes = g.bank + 2 * nbuf * g.plane + 128;
   return g;
+}
+// three buffers when they fit next to the bank image (the offline kernels), else two
+inline H4Shape h4_shape_deep(int M, int jlo, int kt, bool pair, bool synthesis) {
+  const H4Shape g = h4_shape(M, jlo, kt, pair, synthesis, 3);
+  return (g.rows <= kH4MaxPlaneRows && g.bytes <= 227 * 1024) ? g : h4_shape(M, jlo, kt, pair, synthesis, 2);
 }
 inline bool h4_shape_fits(const H4Shape& g) { return g.rows <= kH4MaxPlaneRows && g.bytes <= 227 * 1024; }
 
-// one elected lane: the MMAs of a tile, D[:, 0:128] = h1 [c1 | c2]^T, D[:, 0:64] += h2 c1^T.  The first `tlo` and last `thi`
+// one elected lane: the MMAs of a tile, D[:, 0:128] = h1 [c1 | c2']^T, D[:, 64:128] += h2' c1^T.  The first `tlo` and last `thi`
 // K-steps carry only the tails of the prototype: there the two correction terms (h1 c2, h2 c1) are below the error budget
 // that pqmf_build_tables_f32 checked against the actual bank, so those steps run h1 c1 alone (N = 64) and no h2 pass.
+// (Issue order matters: all N = 128 MMAs, then all N = 64 ones -- alternating the two shapes was measured slower,
+// experiments/probe_mma_order.cu.)
 // `pad_bytes` shifts the A windows (synthesis alignment).
 template <bool PAIR>
 __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_addr, uint32_t plane2_addr, uint32_t bank_addr, int ks,
@@ -90,14 +111,27 @@ __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_a
     const uint32_t byte = 32u * (uint32_t)s + (uint32_t)pad_bytes;
     return (uint64_t)(8u * (byte >> 7) + ((byte >> 4) & 7u));
   };
-  auto mma = [&](uint64_t a, uint64_t bdesc, uint32_t idesc, bool acc) {
-    if constexpr (PAIR) ptx::umma_pair_f16(d_tmem, a, bdesc, idesc, acc);
-    else ptx::umma_f16(d_tmem, a, bdesc, idesc, acc);
+  auto mma = [&](uint32_t d, uint64_t a, uint64_t bdesc, uint32_t idesc, bool acc) {
+    if constexpr (PAIR) ptx::umma_pair_f16(d, a, bdesc, idesc, acc);
+    else ptx::umma_f16(d, a, bdesc, idesc, acc);
   };
-  for (int s = tlo; s < ks - thi; ++s) mma(da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != tlo);  // initialises all 128 columns
-  for (int s = 0; s < tlo; ++s) mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
-  for (int s = ks - thi; s < ks; ++s) mma(da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
-  for (int s = tlo; s < ks - thi; ++s) mma(da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = tlo; s < ks - thi; ++s) mma(d_tmem, da1 + a_step(s), db + (uint64_t)(kStep * s), idesc128, s != tlo);  // initialises all 128 columns
+  for (int s = 0; s < tlo; ++s) mma(d_tmem, da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = ks - thi; s < ks; ++s) mma(d_tmem, da1 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);
+  for (int s = tlo; s < ks - thi; ++s) mma(d_tmem + 64u, da2 + a_step(s), db64 + (uint64_t)(kStep * s), idesc64, true);  // second-term columns
+}
+
+// two-term fp16 split of a pair with the residual scaled into the normal range: v = h1 + 2^-11 h2' (exact residual, |h2'| <= |v|)
+__device__ __forceinline__ void split2_f16s(float a, float b, uint32_t& h1_bits, uint32_t& h2_bits) {
+  const __half2 h1 = __floats2half2_rn(a, b);
+  const float2 h1f = __half22float2(h1);
+  const __half2 h2 = __floats2half2_rn((a - h1f.x) * kH4Res, (b - h1f.y) * kH4Res);
+  h1_bits = *reinterpret_cast<const uint32_t*>(&h1);
+  h2_bits = *reinterpret_cast<const uint32_t*>(&h2);
+}
+// accumulator columns -> value: 2^-10 (D0 + 2^-11 D1)
+__device__ __forceinline__ float h4_combine(uint32_t d0, uint32_t d1) {
+  return fmaf(__uint_as_float(d1), 1.0f / kH4Res, __uint_as_float(d0)) * (1.0f / (float)(1 << kH16ScaleLog2));
 }
 
 template <int N>
@@ -126,9 +160,9 @@ __device__ __forceinline__ H4Smem h4_carve(unsigned char* smem, const H4Shape& g
   H4Smem s;
   s.bank = smem;
   s.planes = smem + g.bank;
-  s.pfull = reinterpret_cast<uint64_t*>(smem + g.bank + 4 * g.plane);  // [2]
-  s.mma_bar = s.pfull + 2;                                              // [2]
-  s.bankfull = s.mma_bar + 2;
+  s.pfull = reinterpret_cast<uint64_t*>(smem + g.bank + 2 * g.nbuf * g.plane);  // [3]
+  s.mma_bar = s.pfull + 3;                                                       // [3]
+  s.bankfull = s.mma_bar + 3;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bankfull + 1);
   return s;
 }
@@ -141,10 +175,10 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
   const int warp = tid >> 5;
   ptx::grid_dep_launch();  // the next kernel in the stream may set itself up while this one is still running
   if (tid == 0) {
-    ptx::mbar_init(&s.pfull[0], worker_warps * (PAIR ? 2 : 1));
-    ptx::mbar_init(&s.pfull[1], worker_warps * (PAIR ? 2 : 1));
-    ptx::mbar_init(&s.mma_bar[0], 1);
-    ptx::mbar_init(&s.mma_bar[1], 1);
+    for (int i = 0; i < 3; ++i) {
+      ptx::mbar_init(&s.pfull[i], worker_warps * (PAIR ? 2 : 1));
+      ptx::mbar_init(&s.mma_bar[i], 1);
+    }
     ptx::mbar_init(s.bankfull, 1);
     ptx::fence_barrier_init();
     // the bank image streams in while the TMEM allocation and the barriers below complete
@@ -152,10 +186,11 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
     ptx::bulk_g2s(s.bank, reinterpret_cast<const unsigned char*>(bank_images) + (size_t)rank * g.bank, (uint32_t)g.bank, s.bankfull);
   }
   if (warp == 0) {
+    const uint32_t cols = g.nbuf > 2 ? 512u : 256u;  // 128 columns per accumulator, a power of two
     if constexpr (PAIR) {
-      ptx::tmem_alloc_pair(s.tmem_slot, 256);
+      ptx::tmem_alloc_pair(s.tmem_slot, cols);
     } else {
-      ptx::tmem_alloc(s.tmem_slot, 256);
+      ptx::tmem_alloc(s.tmem_slot, cols);
       ptx::tmem_relinquish();
     }
   }
@@ -168,14 +203,15 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
 }
 
 template <bool PAIR>
-__device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp) {
+__device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp, int nbuf) {
+  const uint32_t cols = nbuf > 2 ? 512u : 256u;
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) {
     ptx::cluster_sync_all();  // the peer may still be read by / signalled from the leader's last MMAs
-    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
+    if (warp == 0) ptx::tmem_dealloc_pair(tmem, cols);
   } else {
-    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+    if (warp == 0) ptx::tmem_dealloc(tmem, cols);
   }
 }
 
@@ -185,9 +221,10 @@ template <bool PAIR>
 __device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g, uint32_t tmem, unsigned n_iter, int pad_bytes, int tlo,
                                                int thi) {
   const uint32_t bank_addr = ptx::smem_u32(s.bank), plane_addr = ptx::smem_u32(s.planes);
+  const unsigned nbuf = (unsigned)g.nbuf;
   for (unsigned it = 0; it < n_iter; ++it) {
-    const int pb = (int)(it & 1);
-    ptx::mbar_wait(&s.pfull[pb], (it >> 1) & 1);
+    const int pb = (int)(it % nbuf);
+    ptx::mbar_wait(&s.pfull[pb], (it / nbuf) & 1);
     ptx::tc_fence_after();
     if (ptx::elect_one_sync()) {
       h4_issue_mmas<PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * g.plane, plane_addr + (2 * pb + 1) * g.plane, bank_addr, g.ks,
@@ -225,6 +262,7 @@ struct H4AnalysisParams {
   int trim_lo, trim_hi;  // edge K-steps without correction terms (h4_issue_mmas)
   int accumulate;        // add to what y already holds (second launch of a bank split in two tap ranges)
   int keep_in_l2;        // store y without the streaming hint: a synthesis launch that follows walks the tiles backwards and finds the tail in L2
+  int no_l2_prefetch;    // PQMF_FLAG_NO_PREFETCH: skip the L2 prefetch of tile it + 2 (measurement)
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -234,9 +272,9 @@ struct H4AnalysisParams {
 
 template <int M, bool PAIR>
 __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisParams p) {
-  constexpr int FR = 64 / M;                                                // frames per 64-sample row
-  constexpr int HB = M / 2;                                                 // bands per epilogue thread
-  constexpr int NQ = (kH4MaxPlaneRows * 16 + kH4Workers - 1) / kH4Workers;  // float4 loads per thread per tile (row = 16 quads)
+  constexpr int FR = 64 / M;                                               // frames per 64-sample row
+  constexpr int HB = M / 2;                                                // bands per epilogue thread
+  constexpr int NO = (kH4MaxPlaneRows * 8 + kH4Workers - 1) / kH4Workers;  // 8-sample loads per thread per tile (a row is 8 of them)
   extern __shared__ __align__(1024) unsigned char h4_smem[];
   const H4Shape g = p.g;
   const H4Smem sm = h4_carve(h4_smem, g);
@@ -260,37 +298,51 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
   if (warp == kMmaWarp) {
     if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim_lo, p.trim_hi);
   } else {
-    const int n_quads = g.rows * 16;
-    // this thread's share of the fp32 window of a tile, prefetched one tile ahead straight from global memory.  (Two tiles ahead
-    // in two register sets was measured on the same box: 6 % slower in bursts and sustained -- the extra live registers cost more
-    // than the latency they hide.)
-    float4 x0[NQ];
-    auto load_window = [&](float4 (&xr)[NQ], unsigned bb, unsigned cc) {
+    const int n_octs = g.rows * 8;
+    // this thread's share of the fp32 window of a tile (8 consecutive samples per 256-bit load), prefetched one tile ahead straight
+    // from global memory.  (Two tiles ahead in two register sets was measured on the same box: 6 % slower in bursts and sustained --
+    // the extra live registers cost more than the latency they hide.  The depth comes from the L2 prefetch below instead.)
+    float x0[NO][8];
+    auto load_window = [&](unsigned bb, unsigned cc) {
       const long s0 = (long)cc * kH4TileSamples + g.jlo - p.off;
       const float* xrow = p.x + (size_t)bb * p.T;
 #pragma unroll
-      for (int r = 0; r < NQ; ++r) {
-        const int q = tid + kH4Workers * r;
-        const long s = s0 + 4L * q;
-        xr[r] = (bb < n_rows && q < n_quads && s >= 0 && s < p.T) ? ptx::ldg128_na(reinterpret_cast<const float4*>(xrow + s))
-                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < NO; ++r) {
+        const int o = tid + kH4Workers * r;
+        const long s = s0 + 8L * o;
+        if (bb < n_rows && o < n_octs && s >= 0 && s < p.T) {
+          ptx::ldg256_na(xrow + s, x0[r]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x0[r][e] = 0.f;
+        }
       }
     };
-    // fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples).  planes[pb] were last read by the MMAs of tile it-2,
-    // whose completion this thread observed before draining tile it-2.
-    auto convert = [&](const float4 (&xr)[NQ], int pb) {
+    // one thread asks the L2 for the window of the tile after next: by the time the register prefetch of that tile is issued, a
+    // DRAM latency spike has been absorbed (L2 hit ~300 cycles instead of a DRAM access under 75 % bandwidth load)
+    auto l2_prefetch = [&](unsigned bb, unsigned cc) {
+      if (tid != 0 || p.no_l2_prefetch || bb >= n_rows) return;
+      const long s0 = (long)cc * kH4TileSamples + g.jlo - p.off;
+      const long lo = s0 < 0 ? 0 : s0, hi = s0 + g.rows * 64 < p.T ? s0 + g.rows * 64 : p.T;
+      if (hi > lo) ptx::bulk_prefetch_l2(p.x + (size_t)bb * p.T + lo, (uint32_t)(hi - lo) * 4u);
+    };
+    // fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples, one 16-byte chunk per load).  planes[pb] were last read by
+    // the MMAs of tile it-2, whose completion this thread observed before draining tile it-2.
+    auto convert = [&](int pb) {
       unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
       unsigned char* p2 = p1 + g.plane;
 #pragma unroll
-      for (int r = 0; r < NQ; ++r) {
-        const int q = tid + kH4Workers * r;
-        if (q < n_quads) {
-          uint2 a, bq;
-          split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
-          split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
-          const uint32_t o = sw128_offset((uint32_t)q * 8u);
-          *reinterpret_cast<uint2*>(p1 + o) = a;
-          *reinterpret_cast<uint2*>(p2 + o) = bq;
+      for (int r = 0; r < NO; ++r) {
+        const int o = tid + kH4Workers * r;
+        if (o < n_octs) {
+          uint4 a, bq;
+          split2_f16s(x0[r][0], x0[r][1], a.x, bq.x);
+          split2_f16s(x0[r][2], x0[r][3], a.y, bq.y);
+          split2_f16s(x0[r][4], x0[r][5], a.z, bq.z);
+          split2_f16s(x0[r][6], x0[r][7], a.w, bq.w);
+          const uint32_t off = sw128_offset((uint32_t)o * 16u);
+          *reinterpret_cast<uint4*>(p1 + off) = a;
+          *reinterpret_cast<uint4*>(p2 + off) = bq;
         }
       }
     };
@@ -308,7 +360,6 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       const int i = tid & 127, hb = tid >> 7;
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + HB * hb);
       const long n = ((long)cc * kH4Rows + i) * FR;
-      const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
       uint32_t r0[FR][HB], r1[FR][HB];
 #pragma unroll
       for (int dl = 0; dl < FR; ++dl) {
@@ -323,7 +374,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
         const uint32_t flip = (((FR > 1 ? dl : (int)(n & 1)) + p.parity) & 1) == 0 ? 0x80000000u : 0u;
 #pragma unroll
         for (int kk = 0; kk < HB; ++kk) {
-          const float t = (__uint_as_float(r0[dl][kk]) + __uint_as_float(r1[dl][kk])) * scale;
+          const float t = h4_combine(r0[dl][kk], r1[dl][kk]);
           v[dl][kk] = __uint_as_float(__float_as_uint(t) ^ ((kk & 1) ? flip : 0u));
         }
       }
@@ -365,35 +416,40 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       }
     };
 
+    // The workers run up to nbuf - 1 tiles ahead of the accumulator they drain: with three plane pairs / accumulators the tensor pipe
+    // always has a whole tile queued behind the one it is working on, so a late load or a slow store burst in one iteration no
+    // longer leaves it idle (two buffers: period 2685 cycles against 2249 of MMA time per tile, experiments/trace_h4.cu).
+    const unsigned nbuf = (unsigned)g.nbuf, lag = nbuf - 1;
+    auto drain = [&](unsigned k) {
+      const int db = (int)(k % nbuf);
+      ptx::mbar_wait(&sm.mma_bar[db], (k / nbuf) & 1);
+      ptx::tc_fence_after();
+      const unsigned long long t = blockIdx.x + (unsigned long long)k * gridDim.x;
+      const unsigned bb = (unsigned)(t / tpr), cc = (unsigned)(t % tpr);
+      if (bb < n_rows) epilogue(bb, cc, db);
+    };
     unsigned b1 = b, c1 = c;  // tile it + 1
     advance(b1, c1);
-    load_window(x0, b, c);
-    unsigned prev_b = 0, prev_c = 0;
+    unsigned b2 = b1, c2 = c1;  // tile it + 2
+    advance(b2, c2);
+    load_window(b, c);
+    if (n_iter > 1) l2_prefetch(b1, c1);
     for (unsigned it = 0; it < n_iter; ++it) {
-      const int pb = (int)(it & 1);
+      const int pb = (int)(it % nbuf);
       H4_STAMP(0);
-      convert(x0, pb);
+      convert(pb);  // planes[pb] were last read by the MMAs of tile it - nbuf, drained (hence observed complete) in iteration it - 1
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
-      if (it + 1 < n_iter) load_window(x0, b1, c1);  // consumed at the top of the next iteration
+      if (it + 1 < n_iter) load_window(b1, c1);  // consumed at the top of the next iteration
+      if (it + 2 < n_iter) l2_prefetch(b2, c2);
       H4_STAMP(2);
-      H4_STAMP(3);
-      if (it > 0) {
-        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-        ptx::tc_fence_after();
-        H4_STAMP(4);
-        if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
-      }
+      if (it >= lag) drain(it - lag);
       H4_STAMP(5);
-      prev_b = b;
-      prev_c = c;
-      b = b1;
-      c = c1;
-      advance(b1, c1);
+      b1 = b2;
+      c1 = c2;
+      advance(b2, c2);
     }
-    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-    ptx::tc_fence_after();
-    if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+    for (unsigned k = n_iter > lag ? n_iter - lag : 0; k < n_iter; ++k) drain(k);
   }  // workers
 #ifdef PQMF_H4_TRACE
   __syncthreads();
@@ -404,7 +460,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     p.trace[64 * 64 + 2 * blockIdx.x + 1] = t1 - cta_t0;
   }
 #endif
-  h4_teardown<PAIR>(tmem, warp);
+  h4_teardown<PAIR>(tmem, warp, g.nbuf);
 }
 
 // =============================================================================================
@@ -420,6 +476,7 @@ struct H4SynthesisParams {
   int trim_lo, trim_hi;
   int accumulate;        // add to what out already holds
   int reverse;           // walk the tiles from the last to the first (see H4AnalysisParams::keep_in_l2)
+  int no_l2_prefetch;
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -486,8 +543,27 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         }
       }
     };
+    // threads 0 .. M-1 ask the L2 for one band row each of the tile after next (see h4_analysis_kernel)
+    auto l2_prefetch = [&](unsigned bb, unsigned cc) {
+      if (tid >= M || p.no_l2_prefetch || bb >= n_rows) return;
+      if (p.reverse) {
+        bb = n_rows - 1 - bb;
+        cc = tpr - 1 - cc;
+      }
+      const long n0 = (long)cc * (kH4Rows * FR) + nbase, n1 = n0 + ((g.rows * FR + 3) & ~3);
+      const long lo = n0 < 0 ? 0 : n0, hi = n1 < p.F ? n1 : p.F;
+      if (hi > lo) ptx::bulk_prefetch_l2(p.s + ((size_t)bb * M + tid) * p.F + lo, (uint32_t)(hi - lo) * 4u);
+    };
     // sigma(k, n): odd bands (odd kk) flip on even global frames; quads start on multiples of 4, so the parity is j's
     const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
+    auto advance = [&](unsigned& bb, unsigned& cc) {
+      bb += step_b;
+      cc += step_c;
+      if (cc >= tpr) {
+        cc -= tpr;
+        ++bb;
+      }
+    };
     auto convert = [&](const float4 (&v)[8], int pb) {
       if (!has_item) return;
       unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
@@ -514,20 +590,12 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
           o = sw128_offset((uint32_t)(8 * fq + 2 * j) * (2u * M));
         }
         uint4 h1, h2;
-        split2_f16(w[0], w[1], h1.x, h2.x);
-        split2_f16(w[2], w[3], h1.y, h2.y);
-        split2_f16(w[4], w[5], h1.z, h2.z);
-        split2_f16(w[6], w[7], h1.w, h2.w);
+        split2_f16s(w[0], w[1], h1.x, h2.x);
+        split2_f16s(w[2], w[3], h1.y, h2.y);
+        split2_f16s(w[4], w[5], h1.z, h2.z);
+        split2_f16s(w[6], w[7], h1.w, h2.w);
         *reinterpret_cast<uint4*>(p1 + o) = h1;
         *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
-      }
-    };
-    auto advance = [&](unsigned& bb, unsigned& cc) {
-      bb += step_b;
-      cc += step_c;
-      if (cc >= tpr) {
-        cc -= tpr;
-        ++bb;
       }
     };
     // D (TMEM) -> out.  Thread (row i, half hb) drains 32 consecutive output samples = four 32-byte chunks, but rows are 256 B
@@ -539,7 +607,6 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         cc = tpr - 1 - cc;
       }
       const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
-      const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
       uint32_t r0[2][16], r1[2][16];
       ptx::tmem_ld16(taddr, r0[0]);
@@ -551,7 +618,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) val[q][e] = (__uint_as_float(r0[q >> 1][8 * (q & 1) + e]) + __uint_as_float(r1[q >> 1][8 * (q & 1) + e])) * scale;
+        for (int e = 0; e < 8; ++e) val[q][e] = h4_combine(r0[q >> 1][8 * (q & 1) + e], r1[q >> 1][8 * (q & 1) + e]);
       const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr)  // lanes r, r ^ 1 swap the off-diagonal chunks of (2 pr, 2 pr + 1)
@@ -586,66 +653,82 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         }
     };
 
+    const unsigned nbuf = (unsigned)g.nbuf, lag = nbuf - 1;  // see h4_analysis_kernel
+    auto drain = [&](unsigned k) {
+      const int db = (int)(k % nbuf);
+      // every worker waits (the planes of this buffer are rewritten next iteration); the ninth warp has no TMEM rows to drain
+      ptx::mbar_wait(&sm.mma_bar[db], (k / nbuf) & 1);
+      ptx::tc_fence_after();
+      const unsigned long long t = blockIdx.x + (unsigned long long)k * gridDim.x;
+      const unsigned bb = (unsigned)(t / tpr), cc = (unsigned)(t % tpr);
+      if (warp < 8 && bb < n_rows) epilogue(bb, cc, db);
+    };
     unsigned b1 = b, c1 = c;
     advance(b1, c1);
+    unsigned b2 = b1, c2 = c1;
+    advance(b2, c2);
     load_frames(v0, b, c);
-    unsigned prev_b = 0, prev_c = 0;
+    if (n_iter > 1) l2_prefetch(b1, c1);
     for (unsigned it = 0; it < n_iter; ++it) {
-      const int pb = (int)(it & 1);
+      const int pb = (int)(it % nbuf);
       H4_STAMP(0);
       convert(v0, pb);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
       if (it + 1 < n_iter) load_frames(v0, b1, c1);
+      if (it + 2 < n_iter) l2_prefetch(b2, c2);
       H4_STAMP(2);
-      H4_STAMP(3);
-      if (it > 0) {
-        // every worker waits (planes[pb ^ 1] are rewritten next iteration); the ninth warp has no TMEM rows to drain
-        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-        ptx::tc_fence_after();
-        H4_STAMP(4);
-        if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
-      }
+      if (it >= lag) drain(it - lag);
       H4_STAMP(5);
-      prev_b = b;
-      prev_c = c;
-      b = b1;
-      c = c1;
-      advance(b1, c1);
+      b1 = b2;
+      c1 = c2;
+      advance(b2, c2);
     }
-    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-    ptx::tc_fence_after();
-    if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+    for (unsigned k = n_iter > lag ? n_iter - lag : 0; k < n_iter; ++k) drain(k);
   }  // workers
-  h4_teardown<PAIR>(tmem, warp);
+  h4_teardown<PAIR>(tmem, warp, g.nbuf);
 }
 
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
+// per-kernel, per-device record of the dynamic shared memory opted into so far.  Several host threads may launch concurrently
+// (one per device in pqmf_roundtrip_host_multi_f32): the values are atomics, and racing threads at worst both set the attribute.
+struct H4Configured {
+  std::atomic<int> bytes[64];
+  H4Configured() {
+    for (auto& b : bytes) b.store(0, std::memory_order_relaxed);
+  }
+};
+inline int h4_sm_count(int dev) {
+  static std::atomic<int> sm_count[64];
+  int n = sm_count[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n = n > 0 ? n : 148;
+    sm_count[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 template <typename Kern>
-inline int h4_configure(Kern kern, int bytes, int (&configured)[64], int& sm_count_out) {
-  static int sm_count[64] = {0};
+inline int h4_configure(Kern kern, int bytes, H4Configured& configured, int& sm_count_out) {
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (sm_count[dev] == 0) {
-    int n = 0;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    sm_count[dev] = n > 0 ? n : 148;
-  }
-  if (configured[dev] < bytes) {  // the opt-in limit only ever grows (shapes with more K-steps need more shared memory)
+  if (configured.bytes[dev].load(std::memory_order_acquire) < bytes) {  // the opt-in limit only ever grows (shapes with more K-steps need more)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return (int)e;
-    configured[dev] = bytes;
+    int seen = configured.bytes[dev].load(std::memory_order_relaxed);
+    while (seen < bytes && !configured.bytes[dev].compare_exchange_weak(seen, bytes, std::memory_order_release)) {
+    }
   }
-  sm_count_out = sm_count[dev];
+  sm_count_out = h4_sm_count(dev);
   return 0;
 }
 
 // one CTA (or CTA pair) per SM, static round-robin over the tiles; PAIR launches clusters of two
 template <bool PAIR, typename Kern, typename Params>
-inline int h4_launch(Kern kern, Params p, int B, long row_samples, int threads, int (&configured)[64], cudaStream_t st) {
+inline int h4_launch(Kern kern, Params p, int B, long row_samples, int threads, H4Configured& configured, cudaStream_t st) {
   int sms = 0;
   if (!h4_shape_fits(p.g)) return -2;
   if (int e = h4_configure(kern, p.g.bytes, configured, sms)) return e;
@@ -679,19 +762,19 @@ inline int h4_launch(Kern kern, Params p, int B, long row_samples, int threads, 
 
 template <int M, bool PAIR>
 int h4_launch_analysis(H4AnalysisParams p, int B, cudaStream_t st) {
-  static int configured[64] = {0};
+  static H4Configured configured;
   return h4_launch<PAIR>(h4_analysis_kernel<M, PAIR>, p, B, p.F * M, kH4Threads, configured, st);
 }
 
 template <int M, bool PAIR>
 int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
-  static int configured[64] = {0};
+  static H4Configured configured;
   return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR>, p, B, p.F * M, kH4SynThreads, configured, st);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host: bank images, fp16 bits in UMMA K-major no-swizzle layout [chunk of 8 K][128 rows][8],
-// rows = part * 64 + delta * M + (band | phase), part 0 = c1, part 1 = c2
+// rows = part * 64 + delta * M + (band | phase), part 0 = c1, part 1 = c2' = 2^11 (2^10 hk - c1)
 // ---------------------------------------------------------------------------------------------
 inline void hankel4_build_banks(const float* hk /*[M][L]*/, int M, int L, int jlo, int kt, uint16_t* img_analysis, uint16_t* img_synthesis) {
   auto bits = [](float v) {
@@ -713,13 +796,13 @@ inline void hankel4_build_banks(const float* hk /*[M][L]*/, int M, int L, int jl
           const int j = kap - M * delta;
           const float v = (j >= 0 && j < kt && jlo + j < L) ? sa * hk[(size_t)q * L + jlo + j] : 0.f;
           const float c1 = __half2float(__float2half_rn(v));
-          img_analysis[at] = part == 0 ? bits(c1) : bits(v - c1);
+          img_analysis[at] = part == 0 ? bits(c1) : bits((v - c1) * kH4Res);
         }
         {  // synthesis: K index = (frame e, band kb) of the [frame][band] plane: lag = delta + ehi - e, tap M lag + q, q = output phase
           const int e = kap / M, kb = kap % M, lag = delta + ehi - e;
           const float v = (lag >= elo && lag <= ehi && M * lag + q < L) ? ss * hk[(size_t)kb * L + M * lag + q] : 0.f;
           const float c1 = __half2float(__float2half_rn(v));
-          img_synthesis[at] = part == 0 ? bits(c1) : bits(v - c1);
+          img_synthesis[at] = part == 0 ? bits(c1) : bits((v - c1) * kH4Res);
         }
       }
 }

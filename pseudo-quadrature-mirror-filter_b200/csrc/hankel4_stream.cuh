@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
         const int u = tid + kH4Workers * r;
         if (u < n_quads) {
           uint2 a, bq;
-          split2_f16(xr[r].x, xr[r].y, a.x, bq.x);
-          split2_f16(xr[r].z, xr[r].w, a.y, bq.y);
+          split2_f16s(xr[r].x, xr[r].y, a.x, bq.x);
+          split2_f16s(xr[r].z, xr[r].w, a.y, bq.y);
           const uint32_t o = sw128_offset((uint32_t)u * 8u);
           *reinterpret_cast<uint2*>(p1 + o) = a;
           *reinterpret_cast<uint2*>(p2 + o) = bq;
@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
     auto epilogue = [&](long tile, int dbuf) {
       const long sidx = tile * sg.spt + et;
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + HB * hb);
-      const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
       uint32_t r0[FR][HB], r1[FR][HB];
 #pragma unroll
       for (int dl = 0; dl < FR; ++dl) {
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
 #pragma unroll
         for (int dl = 0; dl < FR; ++dl) {
           const uint32_t flip = (((dl + p.parity) & 1) == 0 && (kk & 1)) ? 0x80000000u : 0u;  // global frame parity = parity of dl + frame_parity
-          w[dl] = __uint_as_float(__float_as_uint((__uint_as_float(r0[dl][kk]) + __uint_as_float(r1[dl][kk])) * scale) ^ flip);
+          w[dl] = __uint_as_float(__float_as_uint(h4_combine(r0[dl][kk], r1[dl][kk])) ^ flip);
         }
         __stcs(reinterpret_cast<float4*>(yp + (size_t)kk * F), make_float4(w[0], w[1], w[2], w[3]));
       }
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
     ptx::tc_fence_after();
     epilogue(prev_tile, (int)((n_iter - 1) & 1));
   }
-  h4_teardown<PAIR>(tmem, warp);
+  h4_teardown<PAIR>(tmem, warp, g.nbuf);
 }
 
 struct H4SynthesisStreamParams {
@@ -249,10 +248,10 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
           w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
         }
         uint4 h1, h2;
-        split2_f16(w[0], w[1], h1.x, h2.x);
-        split2_f16(w[2], w[3], h1.y, h2.y);
-        split2_f16(w[4], w[5], h1.z, h2.z);
-        split2_f16(w[6], w[7], h1.w, h2.w);
+        split2_f16s(w[0], w[1], h1.x, h2.x);
+        split2_f16s(w[2], w[3], h1.y, h2.y);
+        split2_f16s(w[4], w[5], h1.z, h2.z);
+        split2_f16s(w[6], w[7], h1.w, h2.w);
         const uint32_t o = sw128_offset((uint32_t)(4 * wq + j) * 32u + 16u * bg);
         *reinterpret_cast<uint4*>(p1 + o) = h1;
         *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
@@ -265,7 +264,6 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
     const bool e_rows = et < sg.spt && eq0 < sg.rows_b;
     auto epilogue = [&](long tile, int dbuf) {
       const long sidx = tile * sg.spt + et;
-      const float scale = 1.0f / (float)(1 << kH16ScaleLog2);
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
       uint32_t r0[2][16], r1[2][16];
       ptx::tmem_ld16(taddr, r0[0]);
@@ -277,7 +275,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) val[q][e] = (__uint_as_float(r0[q >> 1][8 * (q & 1) + e]) + __uint_as_float(r1[q >> 1][8 * (q & 1) + e])) * scale;
+        for (int e = 0; e < 8; ++e) val[q][e] = h4_combine(r0[q >> 1][8 * (q & 1) + e], r1[q >> 1][8 * (q & 1) + e]);
       const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr)
@@ -321,12 +319,12 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
     ptx::tc_fence_after();
     if (warp < 8) epilogue(prev_tile, (int)((n_iter - 1) & 1));
   }
-  h4_teardown<PAIR>(tmem, warp);
+  h4_teardown<PAIR>(tmem, warp, g.nbuf);
 }
 
 // launches (CTA pairs; the caller falls back to the fold kernels on any error)
 template <typename Kern, typename Params>
-inline int h4_stream_launch(Kern kern, Params p, int threads, int (&configured)[64], cudaStream_t st) {
+inline int h4_stream_launch(Kern kern, Params p, int threads, H4Configured& configured, cudaStream_t st) {
   int sms = 0;
   if (!h4_shape_fits(p.g)) return -2;
   if (int e = h4_configure(kern, p.g.bytes, configured, sms)) return e;
@@ -350,12 +348,12 @@ inline int h4_stream_launch(Kern kern, Params p, int threads, int (&configured)[
   return (int)cudaLaunchKernelEx(&cfg, kern, p);
 }
 inline int h4_launch_analysis_stream(H4AnalysisStreamParams p, cudaStream_t st) {
-  static int configured[64] = {0};
+  static H4Configured configured;
   p.n_tiles = (p.B + p.s.spt - 1) / p.s.spt;
   return h4_stream_launch(h4_analysis_stream_kernel<true>, p, kH4Threads, configured, st);
 }
 inline int h4_launch_synthesis_stream(H4SynthesisStreamParams p, cudaStream_t st) {
-  static int configured[64] = {0};
+  static H4Configured configured;
   p.n_tiles = (p.B + p.sg.spt - 1) / p.sg.spt;
   return h4_stream_launch(h4_synthesis_stream_kernel<true>, p, kH4SynThreads, configured, st);
 }

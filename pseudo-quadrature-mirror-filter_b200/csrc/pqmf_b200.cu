@@ -135,6 +135,14 @@ struct HostWorkspace {
 HostWorkspace g_host_ws[kMaxDevices];
 std::mutex g_host_mutex;
 
+// Worst-case error the trimmed correction steps of the Hankel kernels may add, per unit of max|input| (hankel4_pick_trim).  Derived
+// from north_star's 1e-5 max-abs tolerance against the reference's fp32 output (tools/trim_budget.py prints the table behind it):
+// analysis 6e-6 -> 5 K-steps per side at the default bank (bound 5.7e-6; measured on audio-scale noise 1.2e-7 rms, 6.4e-7 max, on
+// the adversarial sign-matched signal 1.6e-6); synthesis 1.5e-5 for ALL n_band sub-bands at |s| = 1 with adversarial signs, i.e.
+// 9.8e-6 at the |s| <= 0.65 that sub-bands of audio reach (flute.wav: 0.65) -> 3 K-steps per side (bound 1.44e-5; measured on the
+// reference's sub-bands 6.3e-8 rms, 3.7e-7 max; all bands at full scale with random signs 2.7e-6).  PQMF_FLAG_EXACT keeps every term.
+constexpr double kTrimBudgetAnalysis = 6e-6, kTrimBudgetSynthesis = 1.5e-5;
+
 constexpr long kFoldTableFloats = 512 + 2 * 16 * 32;  // [ g | c1 | c2 ] of the fold + modulation path
 constexpr long kH16ImageFloats = 512L * 16;            // one hankel16 bank image (fp16 [KT/8][32][8]), sized for KT = 512
 constexpr long kH4TableOffset = kFoldTableFloats + 2 * kH16ImageFloats;
@@ -163,7 +171,7 @@ bool use_h4(int B, long F, int M, const float* hist) {
   return hist == nullptr && (long)B * (((long)F * M + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples) >= 96;
 }
 bool h4_analysis_ok(const float* x, const float* y, long T, long F, int M) {
-  return T > 0 && (T % M) == 0 && (T % 4) == 0 && F == T / M && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
+  return T > 0 && (T % M) == 0 && (T % 8) == 0 && F == T / M && ((uintptr_t)x % 32) == 0 && ((uintptr_t)y % 16) == 0;  // 256-bit loads
 }
 bool h4_synthesis_ok(const float* s, const float* out, long F) {
   return F > 0 && (F & 3) == 0 && ((uintptr_t)s % 16) == 0 && ((uintptr_t)out % 32) == 0;
@@ -175,23 +183,37 @@ void h4_taps(unsigned flags, int& jlo, int& kt) {
   kt = 32 * (int)((flags >> 12) & 0x1F);
 }
 
+// offline launches buffer three tiles between the workers and the tensor pipe when shared memory allows (PQMF_H4_NBUF=2 in the
+// environment forces two: measurement aid, read once)
+pqmf::H4Shape offline_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
+  static const bool two = [] {
+    const char* e = getenv("PQMF_H4_NBUF");
+    return e && atoi(e) == 2;
+  }();
+  return two ? pqmf::h4_shape(M, jlo, kt, pair, synthesis) : pqmf::h4_shape_deep(M, jlo, kt, pair, synthesis);
+}
+
 template <int M>
 int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
   const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);  // exact mode: every correction term
   if (flags & PQMF_FLAG_H4_SPLIT) {  // two tap ranges, two launches; only the outer edge of each range may skip the corrections
     for (int half = 0; half < 2; ++half) {
-      p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, false);
+      p.g = offline_shape(M, jlo + half * kt, kt, true, false);
       p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + half * h4_half_floats(M, L));
       p.trim_lo = half ? 0 : trim;
       p.trim_hi = half ? trim : 0;
       p.accumulate = half;
-      if (const int e = pqmf::h4_launch_analysis<M, true>(p, B, st)) return half ? e : PQMF_ERR_UNSUPPORTED;
+      if (const int e = pqmf::h4_launch_analysis<M, true>(p, B, st)) {
+        if (half) return e;
+        (void)cudaGetLastError();  // nothing was launched: the caller falls back to the direct form, which must not see this error
+        return PQMF_ERR_UNSUPPORTED;
+      }
     }
     return 0;
   }
   p.trim_lo = p.trim_hi = trim;
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
-    p.g = pqmf::h4_shape(M, jlo, kt, true, false);
+    p.g = offline_shape(M, jlo, kt, true, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L));
     const int e = pqmf::h4_launch_analysis<M, true>(p, B, st);
     if (e == 0) return 0;
@@ -201,7 +223,7 @@ int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt
     return PQMF_ERR_UNSUPPORTED;  // single-CTA images are only built for n_band 16 / L 512
   } else {
     if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
-    p.g = pqmf::h4_shape(M, jlo, kt, false, false);
+    p.g = offline_shape(M, jlo, kt, false, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
     return pqmf::h4_launch_analysis<M, false>(p, B, st);
   }
@@ -212,6 +234,7 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
   if (kt == 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4AnalysisParams p{};
   p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.keep_in_l2 = 1;
+  p.no_l2_prefetch = (flags & PQMF_FLAG_NO_PREFETCH) ? 1 : 0;
   switch (M) {
     case 4: return h4_analysis_m<4>(p, tables, jlo, kt, B, L, flags, st);
     case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, L, flags, st);
@@ -227,13 +250,17 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
   const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
   if (flags & PQMF_FLAG_H4_SPLIT) {
     for (int half = 0; half < 2; ++half) {
-      p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, true);
+      p.g = offline_shape(M, jlo + half * kt, kt, true, true);
       p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + (2 + half) * h4_half_floats(M, L));
       // synthesis K-steps run from the largest lag (the END of the tap range) down: the outer edge of the low range is its last steps
       p.trim_lo = half ? trim : 0;
       p.trim_hi = half ? 0 : trim;
       p.accumulate = half;
-      if (const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st)) return half ? e : PQMF_ERR_UNSUPPORTED;
+      if (const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st)) {
+        if (half) return e;
+        (void)cudaGetLastError();
+        return PQMF_ERR_UNSUPPORTED;
+      }
     }
     return 0;
   }
@@ -243,7 +270,7 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
     // up one trimmed step to stay inside the error budget that was computed for the other image
     const int variant = (M < 8) ? ((p.o - ((jlo + kt) / M - 1)) & 1) : 0;
     if (variant) p.trim_lo = p.trim_hi = trim > 0 ? trim - 1 : 0;
-    p.g = pqmf::h4_shape(M, jlo, kt + variant * M, true, true);
+    p.g = offline_shape(M, jlo, kt + variant * M, true, true);
     p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + (1 + variant) * h4_pair_floats(M, L));
     const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st);
     if (e == 0) return 0;
@@ -253,7 +280,7 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
     return PQMF_ERR_UNSUPPORTED;
   } else {
     if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
-    p.g = pqmf::h4_shape(M, jlo, kt, false, true);
+    p.g = offline_shape(M, jlo, kt, false, true);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
     return pqmf::h4_launch_synthesis<M, false>(p, B, st);
   }
@@ -264,6 +291,7 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
   if (kt == 0 || off2 % M != 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisParams p{};
   p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0; p.reverse = 1;
+  p.no_l2_prefetch = (flags & PQMF_FLAG_NO_PREFETCH) ? 1 : 0;
   switch (M) {
     case 4: return h4_synthesis_m<4>(p, tables, jlo, kt, B, L, flags, st);
     case 8: return h4_synthesis_m<8>(p, tables, jlo, kt, B, L, flags, st);
@@ -370,12 +398,12 @@ int fast_synthesis(const float* s, const float* hist, float* out, float* hist_ou
 }
 
 bool use_fast(int M, int L, const float* tables, unsigned flags) {
-  return tables != nullptr && !(flags & PQMF_FLAG_NO_SIGN) && pqmf::hankel16_supported(M, L);
+  return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_FP32)) && pqmf::hankel16_supported(M, L);
 }
 // other band counts / prototype lengths: only the offline Hankel kernels exist (streaming, small batches and the sign-less free
 // functions use the direct form); PQMF_FLAG_EXACT keeps them but runs every correction term
 bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
-  return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_FOLD)) && h4_family(M, L);
+  return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_FOLD | PQMF_FLAG_FP32)) && h4_family(M, L);
 }
 
 }  // namespace
@@ -459,8 +487,8 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
       }
     }
     const int kt_all = split ? 2 * kt : kt;
-    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, false, 4e-6);
-    const int trim_s = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, true, 9e-6);
+    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, false, kTrimBudgetAnalysis);
+    const int trim_s = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, true, kTrimBudgetSynthesis);
     if (residual) *residual = 0.0;
     if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s) | (split ? PQMF_FLAG_H4_SPLIT : 0u);
     return PQMF_OK;
@@ -519,10 +547,9 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
   uint16_t* imgp = reinterpret_cast<uint16_t*>(tables_host + kH4PairOffset);
   pqmf::hankel4_pair_image(img4, ks4, imgp);
   pqmf::hankel4_pair_image(img4 + 2 * kH4ImageFloats, ks4, imgp + 2 * kH4PairImageFloats);
-  // edge K-steps of the Hankel-4 kernels that may skip the fp16 correction terms: worst-case added error, per unit of
-  // max|input|, 4e-6 (analysis) / 9e-6 (synthesis, all 16 bands at full scale); typical random-signal error is ~50x lower
-  const int trim_a = pqmf::hankel4_pick_trim(hk_host, 16, 512, jlo, kt, false, 4e-6);
-  const int trim_s = pqmf::hankel4_pick_trim(hk_host, 16, 512, jlo, kt, true, 9e-6);
+  // edge K-steps of the Hankel-4 kernels that may skip the fp16 correction terms (budgets: kTrimBudget*)
+  const int trim_a = pqmf::hankel4_pick_trim(hk_host, 16, 512, jlo, kt, false, kTrimBudgetAnalysis);
+  const int trim_s = pqmf::hankel4_pick_trim(hk_host, 16, 512, jlo, kt, true, kTrimBudgetSynthesis);
   if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s);
   return PQMF_OK;
 }

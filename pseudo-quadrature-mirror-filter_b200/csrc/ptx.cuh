@@ -55,6 +55,10 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// ask the L2 for `bytes` (multiple of 16) at a 16-byte aligned global address; no destination, no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -234,6 +238,12 @@ __device__ __forceinline__ void ldg256_cs(const float* p, float (&v)[8]) {
                : "l"(p));
 }
 
+// streaming 256-bit load that does not allocate in L1; p must be 32-byte aligned
+__device__ __forceinline__ void ldg256_na(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 // streaming 128-bit load that does not allocate in L1 (the L1/shared data banks are the scarce resource of the Hankel kernels)
 __device__ __forceinline__ float4 ldg128_na(const float4* p) {
   float4 v;

@@ -171,6 +171,20 @@ at::Tensor call_synthesis(const at::Tensor& s, const at::Tensor& hk, const at::T
   return op.call(s, hk, tables, delay_frames, flags);
 }
 
+// The tensor-core kernels carry every sample as two fp16 terms: full fp32-like accuracy for values of audio magnitude, but an
+// ABSOLUTE error floor (~2^-36) below it and a range limit above (|v| < 65504).  Gradients have no natural scale (a mean-reduced
+// loss gives 1e-7 .. 1e-9 per sample), so the backward passes normalise them by an exact power of two first: g' = g * 2^-e with
+// e = floor(log2(max|g|)), computed on the device (no host sync), and fold 2^e into the constant the result is multiplied by anyway.
+// With PQMF_FLAG_FP32 the kernels are plain fp32 and no scaling is needed.
+struct GradScale {
+  at::Tensor down, up;  // 0-dim fp32 tensors 2^-e, 2^e
+};
+GradScale grad_scale(const at::Tensor& g) {
+  const at::Tensor amax = at::clamp(g.detach().abs().amax(), 1e-30, 1e30);
+  const at::Tensor e = at::floor(at::log2(amax));
+  return {at::exp2(-e), at::exp2(e)};
+}
+
 struct AnalysisFn : public torch::autograd::Function<AnalysisFn> {
   static at::Tensor forward(torch::autograd::AutogradContext* ctx, const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables,
                             int64_t n_frames, int64_t flags) {
@@ -187,8 +201,13 @@ struct AnalysisFn : public torch::autograd::Function<AnalysisFn> {
     at::Tensor gy = grads[0].contiguous();
     const int64_t F = gy.size(-1), need = (T + M - 1) / M;   // frames whose synthesis output covers [0, T)
     if (need > F) gy = at::constant_pad_nd(gy, {0, need - F});
-    at::Tensor gx = call_synthesis(gy, hk, tables, 0, flags);
-    gx = gx.slice(-1, 0, T) * (1.0 / (double)M);
+    if (flags & PQMF_FLAG_FP32) {
+      at::Tensor gx = call_synthesis(gy, hk, tables, 0, flags);
+      return {gx.slice(-1, 0, T) * (1.0 / (double)M), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
+    }
+    const GradScale sc = grad_scale(gy);
+    at::Tensor gx = call_synthesis(gy * sc.down, hk, tables, 0, flags);
+    gx = gx.slice(-1, 0, T) * (sc.up * (1.0 / (double)M));
     return {gx, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
   }
 };
@@ -208,7 +227,10 @@ struct SynthesisFn : public torch::autograd::Function<SynthesisFn> {
     const int64_t d = ctx->saved_data["delay"].toInt(), flags = ctx->saved_data["flags"].toInt(), M = hk.size(0);
     const at::Tensor g = grads[0].contiguous();          // [B, C, M F]
     const int64_t F = g.size(-1) / M;
-    at::Tensor a = call_analysis(g, hk, tables, F + d, flags);   // [B, C M, F + d]
+    const bool plain = (flags & PQMF_FLAG_FP32) != 0;
+    GradScale sc;
+    if (!plain) sc = grad_scale(g);
+    at::Tensor a = call_analysis(plain ? g : g * sc.down, hk, tables, F + d, flags);   // [B, C M, F + d]
     if (d > 0) {
       a = a.slice(-1, d, F + d);
       if (!(flags & PQMF_FLAG_NO_SIGN) && (d & 1)) {
@@ -216,9 +238,30 @@ struct SynthesisFn : public torch::autograd::Function<SynthesisFn> {
         a = a * sign.view({1, -1, 1});
       }
     }
-    return {a * (double)M, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
+    a = plain ? a * (double)M : a * (sc.up * (double)M);
+    return {a, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
   }
 };
+
+// the streaming ops mutate caller-owned state and have no backward: fail loudly instead of silently cutting the graph
+at::Tensor analysis_stream_autograd(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& state_in,
+                                    at::Tensor state_out, int64_t frame_parity, int64_t flags) {
+  TORCH_CHECK(!(at::GradMode::is_enabled() && x.requires_grad()),
+              "pqmf_b200::analysis_stream is not differentiable (streaming mode carries state across calls); use forward() for training "
+              "or wrap the call in torch.no_grad()");
+  at::AutoDispatchBelowADInplaceOrView guard;
+  static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("pqmf_b200::analysis_stream", "").typed<decltype(analysis_stream)>();
+  return op.call(x, hk, tables, state_in, state_out, frame_parity, flags);
+}
+at::Tensor synthesis_stream_autograd(const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& state_in,
+                                     at::Tensor state_out, int64_t frame_parity, int64_t flags) {
+  TORCH_CHECK(!(at::GradMode::is_enabled() && s.requires_grad()),
+              "pqmf_b200::synthesis_stream is not differentiable (streaming mode carries state across calls); use inverse() for training "
+              "or wrap the call in torch.no_grad()");
+  at::AutoDispatchBelowADInplaceOrView guard;
+  static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("pqmf_b200::synthesis_stream", "").typed<decltype(synthesis_stream)>();
+  return op.call(s, hk, tables, state_in, state_out, frame_parity, flags);
+}
 
 at::Tensor analysis_autograd(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, int64_t flags) {
   return AnalysisFn::apply(x, hk, tables, n_frames, flags);
@@ -254,4 +297,6 @@ TORCH_LIBRARY_IMPL(pqmf_b200, CUDA, m) {
 TORCH_LIBRARY_IMPL(pqmf_b200, Autograd, m) {
   m.impl("analysis", &analysis_autograd);
   m.impl("synthesis", &synthesis_autograd);
+  m.impl("analysis_stream", &analysis_stream_autograd);
+  m.impl("synthesis_stream", &synthesis_stream_autograd);
 }

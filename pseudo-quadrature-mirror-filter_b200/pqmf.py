@@ -31,6 +31,7 @@ _EMPTY = torch.zeros(0)
 # largest |hk - g (x) C| accepted for the fold + modulation factorisation (1.7e-7 for the
 # reference's own banks).  A bank that fails it (e.g. a hand-edited hk) silently uses the direct-form kernels.
 _FOLD_RESIDUAL_LIMIT = 1e-6
+assert _lib.PQMF_FLAG_FP32 == 16
 
 
 def reverse_half(x: torch.Tensor) -> torch.Tensor:
@@ -91,11 +92,15 @@ class PQMF(nn.Module):
     polyphase   : kept for API compatibility -- both settings run the same fused kernel and differ only in
                   the shape checks the reference applies (polyphase needs T % n_band == 0)
     n_channels  : stored, as in the reference; multichannel input is folded into the batch
-    exact       : every term of the registered ``hk`` (Hankel-16 tensor-core kernels at n_band 16, register-tiled direct form
-                  elsewhere) instead of the default kernels, whose error is bounded below the 1e-5 tolerance
+    exact       : every term of the registered ``hk``: no fold factorisation and no trimmed correction steps.  Still the TENSOR-CORE
+                  kernels wherever they exist (samples carried as two fp16 terms: |x| < 65504, absolute error floor ~1e-11)
+    fp32        : plain fp32 arithmetic on the CUDA cores for every shape (the register-tiled direct form): the arithmetic of the
+                  reference's ``conv1d`` -- no range limit, fp32's relative accuracy at any signal level, ~20x slower
+    check_range : debug aid.  The tensor-core kernels assume audio-like magnitudes; with ``check_range=True`` every call first checks
+                  max|x| (one host sync) and routes inputs beyond +-6e4 or entirely below 1e-6 to the fp32 kernels
     """
 
-    def __init__(self, attenuation, n_band, polyphase=True, n_channels=1, exact=False):
+    def __init__(self, attenuation, n_band, polyphase=True, n_channels=1, exact=False, fp32=False, check_range=False):
         super().__init__()
         proto = get_prototype(attenuation, n_band)
         if polyphase:
@@ -109,7 +114,8 @@ class PQMF(nn.Module):
         self.n_band: int = int(n_band)
         self.polyphase: bool = bool(polyphase)
         self.n_channels: int = int(n_channels)
-        self._flags: int = _lib.PQMF_FLAG_EXACT if exact else 0
+        self._flags: int = (_lib.PQMF_FLAG_EXACT if exact else 0) | (_lib.PQMF_FLAG_FP32 if fp32 else 0)
+        self.check_range: bool = bool(check_range)
         self.fold_residual: float = float("nan")
         self.refresh_tables()
         self.register_load_state_dict_post_hook(_refresh_after_load)
@@ -123,8 +129,16 @@ class PQMF(nn.Module):
             # Hankel kernels (which take hk as it is) still do
             fast_flags |= _lib.PQMF_FLAG_NO_FOLD
         self.fold_residual = residual
-        self._flags = (self._flags & _lib.PQMF_FLAG_EXACT) | fast_flags
+        self._flags = (self._flags & (_lib.PQMF_FLAG_EXACT | _lib.PQMF_FLAG_FP32)) | fast_flags
         self._tables = tables.to(self.hk.device)
+
+    def _call_flags(self, x: torch.Tensor) -> int:
+        """Flags for one call: with ``check_range`` inputs outside the comfortable range of the fp16-pair kernels go to fp32."""
+        if self.check_range and x.numel() > 0:
+            peak = float(x.detach().abs().amax().item())
+            if not (1e-6 <= peak < 6.0e4):  # also catches inf / nan
+                return self._flags | 16  # PQMF_FLAG_FP32 (a literal: TorchScript cannot close over module globals)
+        return self._flags
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x [B, 1, T] (or [B, C, T]) -> sub-bands [B, n_band, T / n_band] (or [B, C*n_band, ...])."""
@@ -136,7 +150,7 @@ class PQMF(nn.Module):
         t = x.shape[-1]
         if self.polyphase and t % self.n_band != 0:
             raise RuntimeError("polyphase PQMF needs the number of samples to be a multiple of n_band")
-        return torch.ops.pqmf_b200.analysis(x, self.hk, self._tables, t // self.n_band, self._flags)
+        return torch.ops.pqmf_b200.analysis(x, self.hk, self._tables, t // self.n_band, self._call_flags(x))
 
     @torch.jit.export
     def inverse(self, x: torch.Tensor) -> torch.Tensor:
@@ -145,7 +159,7 @@ class PQMF(nn.Module):
             raise RuntimeError("PQMF.inverse expects a 3-D tensor [batch, n_band, frames]")
         if self.n_band == 1:
             return x
-        return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 0, self._flags)
+        return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 0, self._call_flags(x))
 
     @torch.jit.export
     def process(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -238,7 +252,7 @@ class CachedPQMF(PQMF):
         if self.streaming:
             return self.forward_stream(x)
         n_frames = (x.shape[-1] + self.n_band - 1) // self.n_band
-        return torch.ops.pqmf_b200.analysis(x, self.hk, self._tables, n_frames, self._flags)
+        return torch.ops.pqmf_b200.analysis(x, self.hk, self._tables, n_frames, self._call_flags(x))
 
     @torch.jit.export
     def inverse(self, x: torch.Tensor) -> torch.Tensor:
@@ -248,7 +262,7 @@ class CachedPQMF(PQMF):
             return x
         if self.streaming:
             return self.inverse_stream(x)
-        return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 1, self._flags)
+        return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 1, self._call_flags(x))
 
     @torch.jit.export
     def process(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
