@@ -423,6 +423,47 @@ def bench_config5(torch, pq, dev, seconds):
             "samples_per_step": rows * t, "steps": steps, "ms": ms, "bytes_per_sample": 16}
 
 
+def bench_single_stream_latency(torch, pq, dev):
+    """The reference's real-time use (PQMFWrapper.py:40-41: one stream, host blocks of 512 ... 16384 samples): microseconds per block
+    step (forward_stream + inverse_stream, state carried) -- eager module calls, wall clock including the host side of every call,
+    and CUDA-graph replay (pq.StreamGraph) -- next to the real-time budget of the block at 44.1 kHz."""
+    out = {}
+    for block in (512, 2048, 8192, 16384):
+        mod = pq.CachedPQMF(ATTEN, N_BAND).to(dev)
+        xb = (0.5 * torch.randn(1, 1, block, device=dev)).clamp_(-1, 1)
+        n = 200
+        with torch.no_grad():
+            for _ in range(10):
+                mod.inverse_stream(mod.forward_stream(xb))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                mod.inverse_stream(mod.forward_stream(xb))
+            torch.cuda.synchronize()
+            eager_us = (time.perf_counter() - t0) / n * 1e6
+            g = pq.StreamGraph(pq.CachedPQMF(ATTEN, N_BAND).to(dev), 1, block)
+            for _ in range(10):
+                g.step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                g.step()
+            torch.cuda.synchronize()
+            graph_us = (time.perf_counter() - t0) / n * 1e6
+            # one isolated step, host call to results visible on the host: the latency a real-time caller sees
+            lat = []
+            for _ in range(20):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                g.step()
+                torch.cuda.synchronize()
+                lat.append((time.perf_counter() - t0) * 1e6)
+            lat.sort()
+        out[f"block{block}"] = {"eager_us_per_step": round(eager_us, 1), "graph_us_per_step": round(graph_us, 1), "graph_isolated_step_us_median": round(lat[len(lat) // 2], 1),
+                                "realtime_budget_us_at_44k1": round(block / 44100 * 1e6, 1)}
+    return out
+
+
 def other_configs(torch, dist, pq, dev, mod, x, peak, n_gpus, distributed):
     """The other BASELINE.json configs, SUSTAINED (each timed back to back for ~0.5 s) and at every N (each rank runs its own shard,
     the time is the max over ranks): Msamples/s whole-job and fraction of the per-GPU HBM roofline.  Plus the burst figure of the headline
@@ -445,6 +486,7 @@ def other_configs(torch, dist, pq, dev, mod, x, peak, n_gpus, distributed):
             out["n_band16_burst"] = {"analysis_ms": round(ta, 4), "synthesis_ms": round(ts, 4), "round_trip": round(n / (ta + ts) * 1e-3, 1),
                                      "frac": round(16 * n / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
             del y
+            out["single_stream_latency"] = bench_single_stream_latency(torch, pq, dev)
         out["config3"] = entry(bench_config3(torch, pq, dev, 0.5))
         r4 = bench_config4(torch, pq, dev, 2.0)
         per = {}

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PQMF_B200_ABI_VERSION 1
+#define PQMF_B200_ABI_VERSION 2 /* 2: + pcm16, band table, reconstruct, multi-device host entry, PQMF_FLAG_FP32 */
 
 #define PQMF_OK 0
 #define PQMF_ERR_ARG (-1)         /* null pointer, non-positive size, misaligned buffer ...      */
@@ -51,7 +51,6 @@ extern "C" {
                                * representation of the samples, hence no range limit and fp32's relative accuracy at any signal     *
                                * level -- the arithmetic of the reference's conv1d, ~20x slower than the tensor-core kernels        */
 #define PQMF_FLAG_NO_PAIR 8u  /* n_band 16: launch the Hankel kernels one CTA per SM instead of as CTA pairs (bit-identical)     */
-#define PQMF_FLAG_NO_PREFETCH 64u /* offline Hankel kernels: no L2 prefetch of the tile after next (bit-identical; measurement)        */
 #define PQMF_FLAG_NO_FOLD 32u /* n_band 16: never use the fold + modulation kernels (a bank that is not window x cosine: the     *
                                * Hankel kernels take hk as it is)                                                                */
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* first kept tap / 32, kept taps / 32 */
@@ -103,6 +102,36 @@ int pqmf_analysis_f32(const float* x, float* y, const float* hk, const float* ta
 int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float* tables, int B, long n_frames, int M, int L,
                        int delay_frames, unsigned flags, pqmf_stream_t stream);
 
+/* ---- per-band hand-off of the pitch-shifter pipeline (PitchShifterPvoc/1-PitchShifterWrapper.py:243-295: every
+ *      sub-band goes through its own pitch shifter and comes back as a SEPARATE tensor of its own length; the reference then
+ *      cross-fades each band's first Lx samples with the tail kept from the previous block (:259-276), centre-crops / zero-pads
+ *      it to the analysis frame count (:279-289), concatenates the bands (:295) and calls CachedPQMF.inverse (:297)).
+ * One synthesis call that reads the n_band tensors through a pointer table and applies cross-fade and crop / pad in its loads:
+ *   bands   host array of M device pointers, band k = [B, lens[k]] row-contiguous;  lens  host array of M lengths
+ *   s[b,k,f] = v_k[b, f + (lens[k] - n_frames) / 2]  (lens[k] > n_frames)   or   v_k[b, f - (n_frames - lens[k]) / 2], 0 outside
+ *   v_k[b,u] = prev_tail[k,u] * fade_out[u] + band_k[b,u] * fade_in[u]  for u < Lx  (only when prev_tail != NULL, B == 1 and
+ *              lens[k] >= Lx, as in the reference), band_k[b,u] otherwise
+ *   out = pqmf_synthesis_f32(s, delay_frames);   tail_out[k,:] = v_k[0, lens[k]-Lx:]  (B == 1, lens[k] >= Lx), else prev_tail[k,:]
+ * prev_tail / fade_out / fade_in / tail_out are device pointers ([M, Lx], [Lx], [Lx], [M, Lx]); tail_out must not alias
+ * prev_tail.  M <= 64.  fp32 direct-form arithmetic (the hand-off is a real-time, batch-1 path). */
+int pqmf_synthesis_bands_f32(const float* const* bands, const long* lens, float* out, const float* hk, int B, long n_frames, int M, int L,
+                             int delay_frames, const float* prev_tail, const float* fade_out, const float* fade_in, float* tail_out, int Lx,
+                             unsigned flags, pqmf_stream_t stream);
+
+/* ---- int16 PCM edge (the reference's inputs are the 16-bit WAVs under audio/, loaded by torchaudio.load as
+ *      int16 / 32768 per channel: PQMFWrapper.py:113, 1-PitchShifterWrapper.py:348, PQMFPsWrapper.py:175; 2-TestBlocks.py:26-30
+ *      down-mixes with mean(dim=0)).  The de-interleave and the int16 -> fp32 conversion happen inside the analysis loads, the
+ *      fp32 -> int16 conversion and the interleave inside the synthesis stores: 2 B/sample/channel cross the API instead of 4. ----
+ * pcm [B, T, C] interleaved WAV frames -> y [rows, M, n_frames], rows = B * C (row = clip * C + channel: torchaudio.load's [C, T]
+ * per clip) or, with downmix != 0, rows = B and every row is the mean over the channels (fp32 sum in channel order, then / C).
+ * Bit-identical to pqmf_analysis_f32 on the converted rows. */
+int pqmf_analysis_pcm16(const int16_t* pcm, float* y, const float* hk, const float* tables, int B, long T, int C, int downmix,
+                        long n_frames, int M, int L, unsigned flags, pqmf_stream_t stream);
+/* s [B * C, M, n_frames] -> pcm [B, M * n_frames, C]: pqmf_synthesis_f32 followed by clamp(rint(v * 32768), -32768, 32767)
+ * (round half to even, saturating), interleaved. */
+int pqmf_synthesis_pcm16(const float* s, int16_t* pcm, const float* hk, const float* tables, int B, int C, long n_frames, int M, int L,
+                         int delay_frames, unsigned flags, pqmf_stream_t stream);
+
 /* ---- streaming (cached) mode: what cached_conv's cached padding does for the two layers
  *      CachedPQMF builds at pqmf.py:316-333, with explicit caller-owned state ----
  * analysis: frame n of the block sees samples [n*M - L, n*M) of (history ++ x):
@@ -129,6 +158,16 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
 int pqmf_roundtrip_f32(const float* x, float* y, float* out, const float* hk, const float* tables, int B, long T, long n_frames,
                        int M, int L, int delay_frames, unsigned flags, pqmf_stream_t stream);
 
+/* ---- reconstruction only: the forward of the Pvoc wrapper (1-PitchShifterWrapper.py:303-316: decompose, inverse, return the
+ *      signal) never hands the sub-bands to anyone.  Here they are not an output either: they pass through `scratch`, row chunk
+ *      by row chunk (<= 48 MB of sub-bands per chunk, >= 96 tiles when the batch allows), so that the synthesis launch of a chunk
+ *      reads what the analysis launch just wrote from the 126 MB L2 and the next chunk overwrites the same lines before they are
+ *      written back: 8 B/sample of DRAM traffic instead of 16, and no [B, M, n_frames] allocation.  Bit-identical to
+ *      pqmf_roundtrip_f32's `out`.  scratch: device, >= pqmf_reconstruct_scratch_bytes(B, T, n_frames, M) bytes, caller-owned. */
+size_t pqmf_reconstruct_scratch_bytes(int B, long T, long n_frames, int M);
+int pqmf_reconstruct_f32(const float* x, float* out, float* scratch, size_t scratch_bytes, const float* hk, const float* tables, int B, long T,
+                         long n_frames, int M, int L, int delay_frames, unsigned flags, pqmf_stream_t stream);
+
 /* ---- end-to-end host entry (what a non-torch host -- e.g. the Pure Data external that loads the
  *      reference's .ts, README.md:16 -- would call): host buffers in, host buffers out.
  * Pipelines H2D copy, analysis, synthesis and D2H copy over row chunks on internal streams and
@@ -138,7 +177,21 @@ int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host,
                             const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
                             int device);
 
-/* Frees the per-device staging buffers / streams that pqmf_roundtrip_host_f32 keeps between calls. */
+/* The same with 16-bit PCM on both sides of the link (2 B/sample/channel each way instead of 4): pcm_host [B, T, C] interleaved WAV
+ * frames -> y_host [B * C, M, T/M] (may be NULL) and out_host [B, T, C]; pqmf_analysis_pcm16 / pqmf_synthesis_pcm16 per chunk. */
+int pqmf_roundtrip_host_pcm16(const int16_t* pcm_host, float* y_host, int16_t* out_host, const float* hk_host,
+                              const float* tables_host, int B, long T, int C, int M, int L, int delay_frames, unsigned flags,
+                              int device);
+
+/* Multi-GPU host entry (rows are independent, no collective): splits the B rows into n_devices contiguous shards (sizes
+ * differing by at most one, in the order of `devices`) and runs pqmf_roundtrip_host_f32 for every shard concurrently, one host
+ * thread and one staging workspace per device.  Returns the first non-zero status.  Calls for different devices never serialise
+ * on each other (the workspace lock is per device). */
+int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
+                                  const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
+                                  const int* devices, int n_devices);
+
+/* Frees the per-device staging buffers / streams that the pqmf_roundtrip_host_* entry points keep between calls. */
 void pqmf_host_release(void);
 
 /* Number of kernels the library has launched in this process (bench.py reports it as gpu_launches). */

@@ -25,7 +25,6 @@ PQMF_FLAG_FOLD = 4
 PQMF_FLAG_NO_PAIR = 8
 PQMF_FLAG_FP32 = 16
 PQMF_FLAG_NO_FOLD = 32
-PQMF_FLAG_NO_PREFETCH = 64
 PQMF_FLAG_H4_SPLIT = 1 << 23
 
 
@@ -72,11 +71,26 @@ cabi.pqmf_analysis_stream_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c
 cabi.pqmf_synthesis_stream_f32.restype = ctypes.c_int
 cabi.pqmf_synthesis_stream_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_uint, _vp]
+cabi.pqmf_analysis_pcm16.restype = ctypes.c_int
+cabi.pqmf_analysis_pcm16.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_uint, _vp]
+cabi.pqmf_synthesis_pcm16.restype = ctypes.c_int
+cabi.pqmf_synthesis_pcm16.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_uint, _vp]
 cabi.pqmf_roundtrip_host_f32.restype = ctypes.c_int
 cabi.pqmf_roundtrip_host_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_uint, ctypes.c_int]
+cabi.pqmf_synthesis_bands_f32.restype = ctypes.c_int
+cabi.pqmf_synthesis_bands_f32.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp,
+                                          ctypes.c_int, ctypes.c_uint, _vp]
+cabi.pqmf_roundtrip_host_pcm16.restype = ctypes.c_int
+cabi.pqmf_roundtrip_host_pcm16.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_uint, ctypes.c_int]
+cabi.pqmf_roundtrip_host_multi_f32.restype = ctypes.c_int
+cabi.pqmf_roundtrip_host_multi_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_uint, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
 
-if cabi.pqmf_abi_version() != 1:  # pragma: no cover
+if cabi.pqmf_abi_version() != 2:  # pragma: no cover
     raise ImportError("pqmf_b200: libpqmf_b200.so ABI version mismatch; rebuild")
 
 

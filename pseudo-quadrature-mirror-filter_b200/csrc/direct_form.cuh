@@ -20,9 +20,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pcm.cuh"
+
 namespace pqmf {
 
 constexpr int kDirectThreads = 256;
+
 
 __host__ __device__ inline long floor_div(long a, long b) {
   long q = a / b;
@@ -46,6 +49,7 @@ struct AnalysisDirectParams {
   int QC;        // JC / M
   int xstride;   // row stride (floats) of the polyphase x tile, odd
   int m_shift;   // log2(M) when M is a power of two, else -1
+  PcmIn in;      // in.pcm != nullptr: the rows come from interleaved int16 PCM instead of x
 };
 
 template <int BG, int RF>
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(kDirectThreads) analysis_direct_kernel(Analysi
       const long s = base + u;
       float v = 0.f;
       if (s >= 0) {
-        if (s < p.T) v = __ldg(xrow + s);
+        if (s < p.T) v = p.in.pcm ? pcm_sample(p.in, b, s, p.T) : __ldg(xrow + s);
       } else if (hrow != nullptr && s >= -(long)L) {
         v = __ldg(hrow + L + s);
       }
@@ -143,6 +147,47 @@ __global__ void __launch_bounds__(kDirectThreads) analysis_direct_kernel(Analysi
 // ---------------------------------------------------------------------------------------------
 // synthesis
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxBandTable = 64;
+
+// ---- per-band hand-off of the pitch-shifter pipeline (reference PitchShifterPvoc/1-PitchShifterWrapper.py:243-295).
+// The n_band sub-bands arrive as SEPARATE tensors of different lengths (each band went through its own pitch shifter); the reference
+// cross-fades the first Lx samples of every band with the tail kept from the previous block (:259-276), centre-crops or zero-pads
+// every band to the frame count of the analysis (:279-289), concatenates them (:295) and only then calls inverse.  Here the synthesis
+// kernel reads the bands through this table and applies cross-fade and crop/pad on the fly: no intermediate tensors. ----
+struct BandTable {
+  const float* band[kMaxBandTable];  // band k: [B, len[k]] row-contiguous
+  int len[kMaxBandTable];
+  int start[kMaxBandTable];          // frame f of the synthesis input is sample f + start[k] of band k (negative: left zero padding)
+  const float* prev_tail;            // [M, Lx] or nullptr (no cross-fade)
+  const float* fade_out;             // [Lx]
+  const float* fade_in;              // [Lx]
+  int Lx;
+  int enabled;
+};
+// sub-band frame n of band k, row b, after cross-fade and crop/pad
+__device__ __forceinline__ float band_value(const BandTable& t, int k, long b, long n) {
+  const long u = n + t.start[k];
+  if (u < 0 || u >= t.len[k]) return 0.f;
+  float v = __ldg(t.band[k] + (size_t)b * t.len[k] + u);
+  if (t.prev_tail != nullptr && u < t.Lx && t.len[k] >= t.Lx)
+    v = __fadd_rn(__fmul_rn(__ldg(t.prev_tail + (size_t)k * t.Lx + u), __ldg(t.fade_out + u)), __fmul_rn(v, __ldg(t.fade_in + u)));  // torch: mul, mul, add
+  return v;
+}
+// the tail kept for the next block: the last Lx samples of every band AFTER the cross-fade wrote its prefix (the reference reads the
+// suffix through a view, so for len < 2 Lx it sees blended values); bands shorter than Lx leave their tail unchanged
+__global__ void band_tail_kernel(BandTable t, int M, float* __restrict__ tail_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * t.Lx) return;
+  const int k = idx / t.Lx, j = idx - k * t.Lx;
+  float v = __ldg(t.prev_tail + idx);
+  if (t.len[k] >= t.Lx) {
+    const long u = (long)t.len[k] - t.Lx + j;
+    v = __ldg(t.band[k] + u);
+    if (u < t.Lx) v = __fadd_rn(__fmul_rn(__ldg(t.prev_tail + (size_t)k * t.Lx + u), __ldg(t.fade_out + u)), __fmul_rn(v, __ldg(t.fade_in + u)));
+  }
+  tail_out[idx] = v;
+}
+
 struct SynthesisDirectParams {
   const float* s;     // [B, M, F]
   const float* hist;  // [B, M, K] or nullptr
@@ -156,10 +201,12 @@ struct SynthesisDirectParams {
   int dlo, ND;        // tap-frame range d in [dlo, dlo + ND)
   int hstride;        // floats per band row of the padded bank slice (ND*M + 16)
   int sstride;        // floats per band row of the sub-band tile
+  int16_t* pcm_out;   // != nullptr: write interleaved int16 PCM [clips, M F, C] (row = clip * C + channel) instead of out
+  int C;
+  BandTable bands;    // bands.enabled: the sub-bands come from n_band separate tensors (s unused)
 };
 
 constexpr int kSynthBandsPerChunk = 4;
-
 template <int PG, int RF, bool VEC>
 __global__ void __launch_bounds__(kDirectThreads) synthesis_direct_kernel(SynthesisDirectParams p) {
   constexpr int FL = kDirectThreads / PG;
@@ -205,7 +252,7 @@ __global__ void __launch_bounds__(kDirectThreads) synthesis_direct_kernel(Synthe
       float v = 0.f;
       if (k < M) {
         if (n >= 0) {
-          if (n < p.F) v = __ldg(sb + (size_t)k * p.F + n);
+          if (n < p.F) v = p.bands.enabled ? band_value(p.bands, k, b, n) : __ldg(sb + (size_t)k * p.F + n);
         } else if (hb != nullptr && n >= -(long)p.K) {
           v = __ldg(hb + (size_t)k * p.K + p.K + n);
         }
@@ -246,6 +293,15 @@ __global__ void __launch_bounds__(kDirectThreads) synthesis_direct_kernel(Synthe
   for (int r = 0; r < RF; ++r) {
     const long f = f0 + tf + r * FL;
     if (f >= p.F) continue;
+    if (p.pcm_out != nullptr) {
+      const long clip = b / p.C;
+      const int ch = b - (int)(clip * p.C);
+      int16_t* q = p.pcm_out + ((size_t)clip * M * p.F + f * M + p0) * p.C + ch;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (p0 + c < M) q[(size_t)c * p.C] = pcm_quantise(acc[r][c] * gain);
+      continue;
+    }
     float* o = ob + f * M + p0;
     if (VEC && p0 + 3 < M) {
       *reinterpret_cast<float4*>(o) = make_float4(acc[r][0] * gain, acc[r][1] * gain, acc[r][2] * gain, acc[r][3] * gain);

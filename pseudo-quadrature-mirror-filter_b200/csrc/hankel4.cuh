@@ -16,14 +16,15 @@
 // (tcgen05.mma issue blocks the issuing thread while the tensor queue is full).  With PAIR the kernel runs as clusters of two
 // CTAs sharing the bank operand (cta_group::2).  DESIGN.md section 5 has the measurements behind each of these choices.
 //
-// Round 2: (a) The second fp16 term of every sample and the second term of the bank are scaled by 2^11 (h2' = 2^11 (x - h1),
+// Round 2: the second fp16 term of every sample and the second term of the bank are scaled by 2^11 (h2' = 2^11 (x - h1),
 // c2' = 2^11 (2^10 hk - c1)) and accumulate in their own TMEM columns: D[:, 0:64] = h1 c1, D[:, 64:128] = h1 c2' + h2' c1, result =
 // 2^-10 (D0 + 2^-11 D1).  Same MMA count, but the residuals stay in the fp16 normal range: the absolute error floor drops from 2^-25 to
-// 2^-36 per sample.  (b) One thread asks the L2 for the input of tile it + 2 (cp.async.bulk.prefetch.L2) while the workers prefetch
-// tile it + 1 into registers: the per-tile timeline (experiments/trace_h4.cu) showed the tensor pipe busy 2380 of ~2890 cycles per
-// tile, the rest lost to DRAM-latency spikes that a one-tile register prefetch cannot absorb.  (Staging the fp32 input in a shared-
-// memory ring by bulk copies instead -- deeper, no registers -- was built and measured: bit-identical and 7-9 % SLOWER, because shared-
-// memory bandwidth is the binding resource here: the tensor pipe already reads ~250 KB of operands per tile, and the ring adds 69 KB.)
+// 2^-36 per sample.  The analysis window is loaded 8 samples (256 bits) at a time.
+// Measured on one box against this file and NOT kept (bench.py's 20-step loop, medians of 4 alternating runs): the
+// fp32 input staged in a shared-memory ring by bulk copies two tiles ahead (bit-identical, 7-9 % slower: shared-memory bandwidth is
+// the binding resource -- the tensor pipe already reads ~250 KB of operands per tile); an L2 prefetch of the tile after next
+// (cp.async.bulk.prefetch.L2: analysis -3 %, synthesis +14 %); three plane pairs / accumulators so the workers run two tiles ahead
+// (+2 %): the board is power-capped during these kernels, extra activity costs clock.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -34,6 +35,7 @@
 #include <atomic>
 
 #include "hankel16.cuh"
+#include "pcm.cuh"
 #include "ptx.cuh"
 
 namespace pqmf {
@@ -68,10 +70,9 @@ struct H4Shape {
   int jlo, kt, ks;     // first non-zero tap, taps kept (multiples of 32), K-steps = ceil((kt + 64 - M) / 16)
   int rows, plane;     // 128-byte rows of one fp16 plane, bytes per plane (multiple of 1024)
   int bank;            // bytes of one CTA's bank image: [2 ks chunks][96 or 128 rows][16 B]
-  int nbuf;            // plane pairs in shared memory = accumulators in TMEM (2 or 3): how far the workers may run ahead of the tensor pipe
   int bytes;           // dynamic shared memory
 };
-inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis, int nbuf = 2) {
+inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
   H4Shape g;
   g.jlo = jlo;
   g.kt = kt;
@@ -80,14 +81,8 @@ inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis, int n
   g.rows = kH4Rows + (32 * g.ks + pad_bytes - 1) / 128;
   g.plane = ((g.rows * 128 + 1023) / 1024) * 1024;
   g.bank = g.ks * 2 * (pair ? 96 : 128) * 16;
-  g.nbuf = nbuf;
-  g.bytes = g.bank + 2 * nbuf * g.plane + 128;
+  g.bytes = g.bank + 4 * g.plane + 128;
   return g;
-}
-// three buffers when they fit next to the bank image (the offline kernels), else two
-inline H4Shape h4_shape_deep(int M, int jlo, int kt, bool pair, bool synthesis) {
-  const H4Shape g = h4_shape(M, jlo, kt, pair, synthesis, 3);
-  return (g.rows <= kH4MaxPlaneRows && g.bytes <= 227 * 1024) ? g : h4_shape(M, jlo, kt, pair, synthesis, 2);
 }
 inline bool h4_shape_fits(const H4Shape& g) { return g.rows <= kH4MaxPlaneRows && g.bytes <= 227 * 1024; }
 
@@ -125,7 +120,9 @@ __device__ __forceinline__ void h4_issue_mmas(uint32_t d_tmem, uint32_t plane1_a
 __device__ __forceinline__ void split2_f16s(float a, float b, uint32_t& h1_bits, uint32_t& h2_bits) {
   const __half2 h1 = __floats2half2_rn(a, b);
   const float2 h1f = __half22float2(h1);
-  const __half2 h2 = __floats2half2_rn((a - h1f.x) * kH4Res, (b - h1f.y) * kH4Res);
+  // (v - h1) 2^11 as one packed FMA on the pre-scaled value: both products are exact (powers of two) and so is their difference
+  const float2 r = __ffma2_rn(h1f, make_float2(-kH4Res, -kH4Res), __fmul2_rn(make_float2(a, b), make_float2(kH4Res, kH4Res)));
+  const __half2 h2 = __floats2half2_rn(r.x, r.y);
   h1_bits = *reinterpret_cast<const uint32_t*>(&h1);
   h2_bits = *reinterpret_cast<const uint32_t*>(&h2);
 }
@@ -160,9 +157,9 @@ __device__ __forceinline__ H4Smem h4_carve(unsigned char* smem, const H4Shape& g
   H4Smem s;
   s.bank = smem;
   s.planes = smem + g.bank;
-  s.pfull = reinterpret_cast<uint64_t*>(smem + g.bank + 2 * g.nbuf * g.plane);  // [3]
-  s.mma_bar = s.pfull + 3;                                                       // [3]
-  s.bankfull = s.mma_bar + 3;
+  s.pfull = reinterpret_cast<uint64_t*>(smem + g.bank + 4 * g.plane);  // [2]
+  s.mma_bar = s.pfull + 2;                                              // [2]
+  s.bankfull = s.mma_bar + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bankfull + 1);
   return s;
 }
@@ -175,7 +172,7 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
   const int warp = tid >> 5;
   ptx::grid_dep_launch();  // the next kernel in the stream may set itself up while this one is still running
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s.pfull[i], worker_warps * (PAIR ? 2 : 1));
       ptx::mbar_init(&s.mma_bar[i], 1);
     }
@@ -186,11 +183,10 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
     ptx::bulk_g2s(s.bank, reinterpret_cast<const unsigned char*>(bank_images) + (size_t)rank * g.bank, (uint32_t)g.bank, s.bankfull);
   }
   if (warp == 0) {
-    const uint32_t cols = g.nbuf > 2 ? 512u : 256u;  // 128 columns per accumulator, a power of two
     if constexpr (PAIR) {
-      ptx::tmem_alloc_pair(s.tmem_slot, cols);
+      ptx::tmem_alloc_pair(s.tmem_slot, 256);
     } else {
-      ptx::tmem_alloc(s.tmem_slot, cols);
+      ptx::tmem_alloc(s.tmem_slot, 256);
       ptx::tmem_relinquish();
     }
   }
@@ -203,15 +199,14 @@ __device__ __forceinline__ uint32_t h4_prologue(const H4Smem& s, const H4Shape& 
 }
 
 template <bool PAIR>
-__device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp, int nbuf) {
-  const uint32_t cols = nbuf > 2 ? 512u : 256u;
+__device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp) {
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) {
     ptx::cluster_sync_all();  // the peer may still be read by / signalled from the leader's last MMAs
-    if (warp == 0) ptx::tmem_dealloc_pair(tmem, cols);
+    if (warp == 0) ptx::tmem_dealloc_pair(tmem, 256);
   } else {
-    if (warp == 0) ptx::tmem_dealloc(tmem, cols);
+    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
   }
 }
 
@@ -221,10 +216,9 @@ template <bool PAIR>
 __device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g, uint32_t tmem, unsigned n_iter, int pad_bytes, int tlo,
                                                int thi) {
   const uint32_t bank_addr = ptx::smem_u32(s.bank), plane_addr = ptx::smem_u32(s.planes);
-  const unsigned nbuf = (unsigned)g.nbuf;
   for (unsigned it = 0; it < n_iter; ++it) {
-    const int pb = (int)(it % nbuf);
-    ptx::mbar_wait(&s.pfull[pb], (it / nbuf) & 1);
+    const int pb = (int)(it & 1);
+    ptx::mbar_wait(&s.pfull[pb], (it >> 1) & 1);
     ptx::tc_fence_after();
     if (ptx::elect_one_sync()) {
       h4_issue_mmas<PAIR>(tmem + (uint32_t)(pb * 128), plane_addr + (2 * pb) * g.plane, plane_addr + (2 * pb + 1) * g.plane, bank_addr, g.ks,
@@ -254,6 +248,7 @@ __device__ __forceinline__ void h4_publish(const H4Smem& s, uint32_t pfull_leade
 // =============================================================================================
 struct H4AnalysisParams {
   const float* x;        // [B, T]
+  PcmIn in;              // PCM instantiation: the rows come from interleaved int16 WAV frames (x unused)
   float* y;              // [B, M, F]
   const uint16_t* bank;  // fp16 image(s), see hankel4_build_banks / hankel4_pair_image
   long T, F;
@@ -262,7 +257,6 @@ struct H4AnalysisParams {
   int trim_lo, trim_hi;  // edge K-steps without correction terms (h4_issue_mmas)
   int accumulate;        // add to what y already holds (second launch of a bank split in two tap ranges)
   int keep_in_l2;        // store y without the streaming hint: a synthesis launch that follows walks the tiles backwards and finds the tail in L2
-  int no_l2_prefetch;    // PQMF_FLAG_NO_PREFETCH: skip the L2 prefetch of tile it + 2 (measurement)
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -270,7 +264,7 @@ struct H4AnalysisParams {
 #endif
 };
 
-template <int M, bool PAIR>
+template <int M, bool PAIR, bool PCM>
 __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisParams p) {
   constexpr int FR = 64 / M;                                               // frames per 64-sample row
   constexpr int HB = M / 2;                                                // bands per epilogue thread
@@ -301,7 +295,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     const int n_octs = g.rows * 8;
     // this thread's share of the fp32 window of a tile (8 consecutive samples per 256-bit load), prefetched one tile ahead straight
     // from global memory.  (Two tiles ahead in two register sets was measured on the same box: 6 % slower in bursts and sustained --
-    // the extra live registers cost more than the latency they hide.  The depth comes from the L2 prefetch below instead.)
+    // the extra live registers cost more than the latency they hide.)
     float x0[NO][8];
     auto load_window = [&](unsigned bb, unsigned cc) {
       const long s0 = (long)cc * kH4TileSamples + g.jlo - p.off;
@@ -311,20 +305,13 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
         const int o = tid + kH4Workers * r;
         const long s = s0 + 8L * o;
         if (bb < n_rows && o < n_octs && s >= 0 && s < p.T) {
-          ptx::ldg256_na(xrow + s, x0[r]);
+          if constexpr (PCM) pcm_load8(p.in, bb, s, p.T, x0[r]);
+          else ptx::ldg256_na(xrow + s, x0[r]);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) x0[r][e] = 0.f;
         }
       }
-    };
-    // one thread asks the L2 for the window of the tile after next: by the time the register prefetch of that tile is issued, a
-    // DRAM latency spike has been absorbed (L2 hit ~300 cycles instead of a DRAM access under 75 % bandwidth load)
-    auto l2_prefetch = [&](unsigned bb, unsigned cc) {
-      if (tid != 0 || p.no_l2_prefetch || bb >= n_rows) return;
-      const long s0 = (long)cc * kH4TileSamples + g.jlo - p.off;
-      const long lo = s0 < 0 ? 0 : s0, hi = s0 + g.rows * 64 < p.T ? s0 + g.rows * 64 : p.T;
-      if (hi > lo) ptx::bulk_prefetch_l2(p.x + (size_t)bb * p.T + lo, (uint32_t)(hi - lo) * 4u);
     };
     // fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples, one 16-byte chunk per load).  planes[pb] were last read by
     // the MMAs of tile it-2, whose completion this thread observed before draining tile it-2.
@@ -416,40 +403,33 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
       }
     };
 
-    // The workers run up to nbuf - 1 tiles ahead of the accumulator they drain: with three plane pairs / accumulators the tensor pipe
-    // always has a whole tile queued behind the one it is working on, so a late load or a slow store burst in one iteration no
-    // longer leaves it idle (two buffers: period 2685 cycles against 2249 of MMA time per tile, experiments/trace_h4.cu).
-    const unsigned nbuf = (unsigned)g.nbuf, lag = nbuf - 1;
-    auto drain = [&](unsigned k) {
-      const int db = (int)(k % nbuf);
-      ptx::mbar_wait(&sm.mma_bar[db], (k / nbuf) & 1);
-      ptx::tc_fence_after();
-      const unsigned long long t = blockIdx.x + (unsigned long long)k * gridDim.x;
-      const unsigned bb = (unsigned)(t / tpr), cc = (unsigned)(t % tpr);
-      if (bb < n_rows) epilogue(bb, cc, db);
-    };
     unsigned b1 = b, c1 = c;  // tile it + 1
     advance(b1, c1);
-    unsigned b2 = b1, c2 = c1;  // tile it + 2
-    advance(b2, c2);
     load_window(b, c);
-    if (n_iter > 1) l2_prefetch(b1, c1);
+    unsigned prev_b = 0, prev_c = 0;
     for (unsigned it = 0; it < n_iter; ++it) {
-      const int pb = (int)(it % nbuf);
+      const int pb = (int)(it & 1);
       H4_STAMP(0);
-      convert(pb);  // planes[pb] were last read by the MMAs of tile it - nbuf, drained (hence observed complete) in iteration it - 1
+      convert(pb);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
       if (it + 1 < n_iter) load_window(b1, c1);  // consumed at the top of the next iteration
-      if (it + 2 < n_iter) l2_prefetch(b2, c2);
       H4_STAMP(2);
-      if (it >= lag) drain(it - lag);
+      if (it > 0) {
+        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+      }
       H4_STAMP(5);
-      b1 = b2;
-      c1 = c2;
-      advance(b2, c2);
+      prev_b = b;
+      prev_c = c;
+      b = b1;
+      c = c1;
+      advance(b1, c1);
     }
-    for (unsigned k = n_iter > lag ? n_iter - lag : 0; k < n_iter; ++k) drain(k);
+    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    if (prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
 #ifdef PQMF_H4_TRACE
   __syncthreads();
@@ -460,7 +440,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     p.trace[64 * 64 + 2 * blockIdx.x + 1] = t1 - cta_t0;
   }
 #endif
-  h4_teardown<PAIR>(tmem, warp, g.nbuf);
+  h4_teardown<PAIR>(tmem, warp);
 }
 
 // =============================================================================================
@@ -469,6 +449,8 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
 struct H4SynthesisParams {
   const float* s;        // [B, M, F]
   float* out;            // [B, M F]
+  int16_t* pcm_out;      // PCM instantiation: interleaved int16 WAV frames [B / C, M F, C] (out unused)
+  int C;
   const uint16_t* bank;
   long F;
   int o;                 // off2 / M: L / (2 M) (PQMF.inverse) or one less (CachedPQMF.inverse)
@@ -476,7 +458,6 @@ struct H4SynthesisParams {
   int trim_lo, trim_hi;
   int accumulate;        // add to what out already holds
   int reverse;           // walk the tiles from the last to the first (see H4AnalysisParams::keep_in_l2)
-  int no_l2_prefetch;
   H4Shape g;
   long tiles_per_row, n_tiles;
 #ifdef PQMF_H4_TRACE
@@ -484,7 +465,7 @@ struct H4SynthesisParams {
 #endif
 };
 
-template <int M, bool PAIR>
+template <int M, bool PAIR, bool PCM>
 __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4SynthesisParams p) {
   constexpr int FR = 64 / M;       // frames per 128-byte plane row ([frame][band] fp16)
   constexpr int NBG = M >= 8 ? M / 8 : 1;     // band groups: a 16-byte chunk is 8 bands of one frame, or (n_band 4) all bands of two frames
@@ -542,17 +523,6 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
           v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)b4 * p.F + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-    };
-    // threads 0 .. M-1 ask the L2 for one band row each of the tile after next (see h4_analysis_kernel)
-    auto l2_prefetch = [&](unsigned bb, unsigned cc) {
-      if (tid >= M || p.no_l2_prefetch || bb >= n_rows) return;
-      if (p.reverse) {
-        bb = n_rows - 1 - bb;
-        cc = tpr - 1 - cc;
-      }
-      const long n0 = (long)cc * (kH4Rows * FR) + nbase, n1 = n0 + ((g.rows * FR + 3) & ~3);
-      const long lo = n0 < 0 ? 0 : n0, hi = n1 < p.F ? n1 : p.F;
-      if (hi > lo) ptx::bulk_prefetch_l2(p.s + ((size_t)bb * M + tid) * p.F + lo, (uint32_t)(hi - lo) * 4u);
     };
     // sigma(k, n): odd bands (odd kk) flip on even global frames; quads start on multiples of 4, so the parity is j's
     const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
@@ -639,6 +609,12 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       // slot q now holds chunk (lane & 3) of row (i & ~3) | q: samples 64 row + 32 hb + 8 (lane & 3) .. + 7 of the tile
       const long total = p.F * M;  // samples per output row (a multiple of 8: the dispatcher requires F % 4 == 0)
       const long t0 = (long)cc * kH4TileSamples + 64 * (i & ~3) + 32 * hb + 8 * (lane & 3);
+      if constexpr (PCM) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (t0 + 64 * q + 7 < total) pcm_store8(p.pcm_out, p.C, bb, t0 + 64 * q, total, val[q]);
+        return;
+      }
       float* op = p.out + (size_t)bb * total + t0;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -653,40 +629,36 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         }
     };
 
-    const unsigned nbuf = (unsigned)g.nbuf, lag = nbuf - 1;  // see h4_analysis_kernel
-    auto drain = [&](unsigned k) {
-      const int db = (int)(k % nbuf);
-      // every worker waits (the planes of this buffer are rewritten next iteration); the ninth warp has no TMEM rows to drain
-      ptx::mbar_wait(&sm.mma_bar[db], (k / nbuf) & 1);
-      ptx::tc_fence_after();
-      const unsigned long long t = blockIdx.x + (unsigned long long)k * gridDim.x;
-      const unsigned bb = (unsigned)(t / tpr), cc = (unsigned)(t % tpr);
-      if (warp < 8 && bb < n_rows) epilogue(bb, cc, db);
-    };
     unsigned b1 = b, c1 = c;
     advance(b1, c1);
-    unsigned b2 = b1, c2 = c1;
-    advance(b2, c2);
     load_frames(v0, b, c);
-    if (n_iter > 1) l2_prefetch(b1, c1);
+    unsigned prev_b = 0, prev_c = 0;
     for (unsigned it = 0; it < n_iter; ++it) {
-      const int pb = (int)(it % nbuf);
+      const int pb = (int)(it & 1);
       H4_STAMP(0);
       convert(v0, pb);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
       if (it + 1 < n_iter) load_frames(v0, b1, c1);
-      if (it + 2 < n_iter) l2_prefetch(b2, c2);
       H4_STAMP(2);
-      if (it >= lag) drain(it - lag);
+      if (it > 0) {
+        // every worker waits (planes[pb ^ 1] are rewritten next iteration); the ninth warp has no TMEM rows to drain
+        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+      }
       H4_STAMP(5);
-      b1 = b2;
-      c1 = c2;
-      advance(b2, c2);
+      prev_b = b;
+      prev_c = c;
+      b = b1;
+      c = c1;
+      advance(b1, c1);
     }
-    for (unsigned k = n_iter > lag ? n_iter - lag : 0; k < n_iter; ++k) drain(k);
+    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
   }  // workers
-  h4_teardown<PAIR>(tmem, warp, g.nbuf);
+  h4_teardown<PAIR>(tmem, warp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -760,16 +732,25 @@ inline int h4_launch(Kern kern, Params p, int B, long row_samples, int threads, 
   }
 }
 
+// the PCM instantiations exist as CTA pairs only (the single-CTA launch is a fallback for contexts that cannot co-schedule pairs)
 template <int M, bool PAIR>
 int h4_launch_analysis(H4AnalysisParams p, int B, cudaStream_t st) {
-  static H4Configured configured;
-  return h4_launch<PAIR>(h4_analysis_kernel<M, PAIR>, p, B, p.F * M, kH4Threads, configured, st);
+  static H4Configured configured[2];
+  if (p.in.pcm != nullptr) {
+    if constexpr (PAIR) return h4_launch<PAIR>(h4_analysis_kernel<M, PAIR, true>, p, B, p.F * M, kH4Threads, configured[1], st);
+    else return -2;
+  }
+  return h4_launch<PAIR>(h4_analysis_kernel<M, PAIR, false>, p, B, p.F * M, kH4Threads, configured[0], st);
 }
 
 template <int M, bool PAIR>
 int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
-  static H4Configured configured;
-  return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR>, p, B, p.F * M, kH4SynThreads, configured, st);
+  static H4Configured configured[2];
+  if (p.pcm_out != nullptr) {
+    if constexpr (PAIR) return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR, true>, p, B, p.F * M, kH4SynThreads, configured[1], st);
+    else return -2;
+  }
+  return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR, false>, p, B, p.F * M, kH4SynThreads, configured[0], st);
 }
 
 // ---------------------------------------------------------------------------------------------

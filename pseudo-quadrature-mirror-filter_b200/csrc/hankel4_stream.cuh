@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
     ptx::tc_fence_after();
     epilogue(prev_tile, (int)((n_iter - 1) & 1));
   }
-  h4_teardown<PAIR>(tmem, warp, g.nbuf);
+  h4_teardown<PAIR>(tmem, warp);
 }
 
 struct H4SynthesisStreamParams {
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
     ptx::tc_fence_after();
     if (warp < 8) epilogue(prev_tile, (int)((n_iter - 1) & 1));
   }
-  h4_teardown<PAIR>(tmem, warp, g.nbuf);
+  h4_teardown<PAIR>(tmem, warp);
 }
 
 // launches (CTA pairs; the caller falls back to the fold kernels on any error)

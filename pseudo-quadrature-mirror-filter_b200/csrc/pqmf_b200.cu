@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "direct_form.cuh"
@@ -59,10 +60,10 @@ int launch_analysis_direct(pqmf::AnalysisDirectParams p, int B, cudaStream_t st)
 }
 
 int analysis_direct(const float* x, const float* hist, float* y, const float* hk, int B, long T, long n_frames, int M, int L,
-                    int off, int parity, int nosign, cudaStream_t st) {
+                    int off, int parity, int nosign, cudaStream_t st, pqmf::PcmIn pcm = pqmf::PcmIn{nullptr, 1, 0}) {
   if (n_frames == 0 || B == 0) return PQMF_OK;
   pqmf::AnalysisDirectParams p{};
-  p.x = x; p.hist = hist; p.y = y; p.hk = hk;
+  p.x = x; p.hist = hist; p.y = y; p.hk = hk; p.in = pcm;
   p.T = T; p.n_frames = n_frames; p.M = M; p.L = L; p.off = off; p.parity = parity & 1; p.nosign = nosign;
   p.m_shift = log2_exact(M);
   int jc = (512 / M) * M;
@@ -94,10 +95,11 @@ int launch_synthesis_direct(pqmf::SynthesisDirectParams p, int B, cudaStream_t s
 }
 
 int synthesis_direct(const float* s, const float* hist, float* out, const float* hk, int B, long F, int M, int L, int off2,
-                     int parity, int nosign, cudaStream_t st) {
+                     int parity, int nosign, cudaStream_t st, int16_t* pcm_out = nullptr, int C = 1, const pqmf::BandTable* bands = nullptr) {
   if (F == 0 || B == 0) return PQMF_OK;
   pqmf::SynthesisDirectParams p{};
-  p.s = s; p.hist = hist; p.out = out; p.hk = hk;
+  p.s = s; p.hist = hist; p.out = out; p.hk = hk; p.pcm_out = pcm_out; p.C = C;
+  if (bands) p.bands = *bands;
   p.F = F; p.M = M; p.L = L; p.K = L / M; p.off2 = off2; p.parity = parity & 1; p.nosign = nosign;
   p.dlo = (int)pqmf::floor_div(-(long)off2, M);
   const int dhi = (int)pqmf::floor_div((long)L - 1 - off2, M);
@@ -121,19 +123,20 @@ int roll_history(const float* old_h, const float* blk, float* new_h, long rows, 
 
 bool bad_dims(int B, long n, int M, int L) { return B < 0 || n < 0 || M < 2 || L < M || L > (1 << 16); }
 
-// per-device staging workspace of the host-buffer entry point (pqmf_roundtrip_host_f32)
+// per-device staging workspace of the host-buffer entry points (pqmf_roundtrip_host_*).  One mutex PER DEVICE: calls for different
+// devices run concurrently (pqmf_roundtrip_host_multi_f32 drives every GPU of the box from one process, one host thread each).
 constexpr int kHostSlots = 4, kMaxDevices = 16;
 struct HostWorkspace {
+  std::mutex mutex;
   cudaStream_t st[kHostSlots] = {};
-  float* d_x[kHostSlots] = {};
-  float* d_y[kHostSlots] = {};
-  float* d_o[kHostSlots] = {};
+  void* d_x[kHostSlots] = {};   // input chunk (fp32 rows or int16 WAV frames)
+  float* d_y[kHostSlots] = {};  // sub-bands of the chunk
+  void* d_o[kHostSlots] = {};   // output chunk
   float* d_bank = nullptr;
   size_t chunk_elems = 0, bank_elems = 0;
   bool streams_ready = false;
 };
 HostWorkspace g_host_ws[kMaxDevices];
-std::mutex g_host_mutex;
 
 // Worst-case error the trimmed correction steps of the Hankel kernels may add, per unit of max|input| (hankel4_pick_trim).  Derived
 // from north_star's 1e-5 max-abs tolerance against the reference's fp32 output (tools/trim_budget.py prints the table behind it):
@@ -183,22 +186,12 @@ void h4_taps(unsigned flags, int& jlo, int& kt) {
   kt = 32 * (int)((flags >> 12) & 0x1F);
 }
 
-// offline launches buffer three tiles between the workers and the tensor pipe when shared memory allows (PQMF_H4_NBUF=2 in the
-// environment forces two: measurement aid, read once)
-pqmf::H4Shape offline_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
-  static const bool two = [] {
-    const char* e = getenv("PQMF_H4_NBUF");
-    return e && atoi(e) == 2;
-  }();
-  return two ? pqmf::h4_shape(M, jlo, kt, pair, synthesis) : pqmf::h4_shape_deep(M, jlo, kt, pair, synthesis);
-}
-
 template <int M>
 int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
   const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);  // exact mode: every correction term
   if (flags & PQMF_FLAG_H4_SPLIT) {  // two tap ranges, two launches; only the outer edge of each range may skip the corrections
     for (int half = 0; half < 2; ++half) {
-      p.g = offline_shape(M, jlo + half * kt, kt, true, false);
+      p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, false);
       p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + half * h4_half_floats(M, L));
       p.trim_lo = half ? 0 : trim;
       p.trim_hi = half ? trim : 0;
@@ -213,7 +206,7 @@ int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt
   }
   p.trim_lo = p.trim_hi = trim;
   if (!(flags & PQMF_FLAG_NO_PAIR)) {
-    p.g = offline_shape(M, jlo, kt, true, false);
+    p.g = pqmf::h4_shape(M, jlo, kt, true, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L));
     const int e = pqmf::h4_launch_analysis<M, true>(p, B, st);
     if (e == 0) return 0;
@@ -223,18 +216,18 @@ int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt
     return PQMF_ERR_UNSUPPORTED;  // single-CTA images are only built for n_band 16 / L 512
   } else {
     if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
-    p.g = offline_shape(M, jlo, kt, false, false);
+    p.g = pqmf::h4_shape(M, jlo, kt, false, false);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset);
     return pqmf::h4_launch_analysis<M, false>(p, B, st);
   }
 }
-int h4_analysis(const float* x, float* y, const float* tables, int B, long T, long F, int M, int L, unsigned flags, cudaStream_t st) {
+int h4_analysis(const float* x, float* y, const float* tables, int B, long T, long F, int M, int L, unsigned flags, cudaStream_t st,
+                pqmf::PcmIn pcm = pqmf::PcmIn{nullptr, 1, 0}) {
   int jlo, kt;
   h4_taps(flags, jlo, kt);
   if (kt == 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4AnalysisParams p{};
-  p.x = x; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.keep_in_l2 = 1;
-  p.no_l2_prefetch = (flags & PQMF_FLAG_NO_PREFETCH) ? 1 : 0;
+  p.x = x; p.in = pcm; p.y = y; p.T = T; p.F = F; p.off = L / 2; p.parity = 0; p.keep_in_l2 = 1;
   switch (M) {
     case 4: return h4_analysis_m<4>(p, tables, jlo, kt, B, L, flags, st);
     case 8: return h4_analysis_m<8>(p, tables, jlo, kt, B, L, flags, st);
@@ -248,9 +241,10 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
 template <int M>
 int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
   const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
+  if ((flags & PQMF_FLAG_H4_SPLIT) && p.pcm_out != nullptr) return PQMF_ERR_UNSUPPORTED;  // the second launch accumulates: not in int16
   if (flags & PQMF_FLAG_H4_SPLIT) {
     for (int half = 0; half < 2; ++half) {
-      p.g = offline_shape(M, jlo + half * kt, kt, true, true);
+      p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, true);
       p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + (2 + half) * h4_half_floats(M, L));
       // synthesis K-steps run from the largest lag (the END of the tap range) down: the outer edge of the low range is its last steps
       p.trim_lo = half ? trim : 0;
@@ -270,7 +264,7 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
     // up one trimmed step to stay inside the error budget that was computed for the other image
     const int variant = (M < 8) ? ((p.o - ((jlo + kt) / M - 1)) & 1) : 0;
     if (variant) p.trim_lo = p.trim_hi = trim > 0 ? trim - 1 : 0;
-    p.g = offline_shape(M, jlo, kt + variant * M, true, true);
+    p.g = pqmf::h4_shape(M, jlo, kt + variant * M, true, true);
     p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + (1 + variant) * h4_pair_floats(M, L));
     const int e = pqmf::h4_launch_synthesis<M, true>(p, B, st);
     if (e == 0) return 0;
@@ -280,18 +274,18 @@ int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int 
     return PQMF_ERR_UNSUPPORTED;
   } else {
     if (!pqmf::hankel16_supported(M, L)) return PQMF_ERR_UNSUPPORTED;
-    p.g = offline_shape(M, jlo, kt, false, true);
+    p.g = pqmf::h4_shape(M, jlo, kt, false, true);
     p.bank = reinterpret_cast<const uint16_t*>(tables + kH4TableOffset + kH4ImageFloats);
     return pqmf::h4_launch_synthesis<M, false>(p, B, st);
   }
 }
-int h4_synthesis(const float* s, float* out, const float* tables, int B, long F, int off2, int M, int L, unsigned flags, cudaStream_t st) {
+int h4_synthesis(const float* s, float* out, const float* tables, int B, long F, int off2, int M, int L, unsigned flags, cudaStream_t st,
+                 int16_t* pcm_out = nullptr, int C = 1) {
   int jlo, kt;
   h4_taps(flags, jlo, kt);
   if (kt == 0 || off2 % M != 0) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisParams p{};
-  p.s = s; p.out = out; p.F = F; p.o = off2 / M; p.parity = 0; p.reverse = 1;
-  p.no_l2_prefetch = (flags & PQMF_FLAG_NO_PREFETCH) ? 1 : 0;
+  p.s = s; p.out = out; p.pcm_out = pcm_out; p.C = C; p.F = F; p.o = off2 / M; p.parity = 0; p.reverse = 1;
   switch (M) {
     case 4: return h4_synthesis_m<4>(p, tables, jlo, kt, B, L, flags, st);
     case 8: return h4_synthesis_m<8>(p, tables, jlo, kt, B, L, flags, st);
@@ -404,6 +398,99 @@ bool use_fast(int M, int L, const float* tables, unsigned flags) {
 // functions use the direct form); PQMF_FLAG_EXACT keeps them but runs every correction term
 bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
   return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_FOLD | PQMF_FLAG_FP32)) && h4_family(M, L);
+}
+
+// ---- host-buffer round trip, generic over the sample format (float rows, or int16 interleaved WAV frames with C channels) ----
+// Row chunks of ~16 MiB of fp32 samples: H2D(i+1), the two kernels of chunk i and D2H(i-1) overlap (PCIe is full duplex), each chunk
+// on its own stream.  The staging buffers live in a per-device workspace that is created on first use and only ever grows, so
+// steady-state calls do no allocation.
+template <typename Sample>
+int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const float* hk_host, const float* tables_host, int B, long T, int C,
+                   int M, int L, int delay_frames, unsigned flags, int device) {
+  constexpr bool kPcm = sizeof(Sample) == 2;
+  if (bad_dims(B, T, M, L) || !x_host || !out_host || !hk_host || (T % M) != 0) return PQMF_ERR_ARG;
+  if (B == 0 || T == 0) return PQMF_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || device >= kMaxDevices) return PQMF_ERR_NO_DEVICE;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  const long F = T / M;
+  static const long chunk_bytes = [] {
+    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 16 MiB of fp32 samples per chunk
+    const long v = e ? atol(e) : 0;
+    return (v > 0 && v <= 1024 ? v : 16L) << 20;
+  }();
+  const long clip_samples = T * C;                      // one clip = C rows of T samples
+  long clips_per_chunk = chunk_bytes / (clip_samples * (long)sizeof(float));
+  if (clips_per_chunk < 1) clips_per_chunk = 1;
+  if (clips_per_chunk > B) clips_per_chunk = B;
+  const size_t chunk_elems = (size_t)clips_per_chunk * clip_samples;
+  const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
+  HostWorkspace& ws = g_host_ws[device];
+  std::lock_guard<std::mutex> lock(ws.mutex);
+  int rc = PQMF_OK;
+  auto check = [&](cudaError_t err) { if (err != cudaSuccess && rc == PQMF_OK) rc = (int)err; return err == cudaSuccess; };
+  if (!ws.streams_ready) {
+    for (int i = 0; i < kHostSlots; ++i) check(cudaStreamCreateWithFlags(&ws.st[i], cudaStreamNonBlocking));
+    ws.streams_ready = (rc == PQMF_OK);
+  }
+  if (rc == PQMF_OK && ws.chunk_elems < chunk_elems) {   // buffers are sized for fp32 samples: int16 chunks fit too
+    for (int i = 0; i < kHostSlots; ++i) {
+      if (ws.d_x[i]) cudaFree(ws.d_x[i]);
+      if (ws.d_y[i]) cudaFree(ws.d_y[i]);
+      if (ws.d_o[i]) cudaFree(ws.d_o[i]);
+      ws.d_x[i] = ws.d_o[i] = nullptr;
+      ws.d_y[i] = nullptr;
+      check(cudaMalloc(&ws.d_x[i], chunk_elems * sizeof(float)));
+      check(cudaMalloc(&ws.d_y[i], chunk_elems * sizeof(float)));
+      check(cudaMalloc(&ws.d_o[i], chunk_elems * sizeof(float)));
+    }
+    ws.chunk_elems = (rc == PQMF_OK) ? chunk_elems : 0;
+  }
+  const size_t bank_elems = (size_t)M * L;
+  if (rc == PQMF_OK && ws.bank_elems < bank_elems + (size_t)n_tab) {
+    if (ws.d_bank) cudaFree(ws.d_bank);
+    ws.d_bank = nullptr;
+    check(cudaMalloc(&ws.d_bank, (bank_elems + (size_t)n_tab) * sizeof(float)));
+    ws.bank_elems = (rc == PQMF_OK) ? bank_elems + (size_t)n_tab : 0;
+  }
+  if (rc != PQMF_OK) return rc;
+  float* d_hk = ws.d_bank;
+  float* d_tab = n_tab ? ws.d_bank + bank_elems : nullptr;
+  // the bank is tiny (<= a few hundred KB): re-send it with every call instead of tracking caller-side changes
+  check(cudaMemcpyAsync(d_hk, hk_host, bank_elems * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
+  if (n_tab) check(cudaMemcpyAsync(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
+  check(cudaStreamSynchronize(ws.st[0]));
+  // Chunk schedule: small chunks at both ends (1/4, 1/4, 1/2 of a chunk ...) shorten the pipeline fill (nothing overlaps the first
+  // H2D) and drain (nothing overlaps the last D2H); full chunks in between keep the kernels efficient.
+  int slot = 0;
+  long clips = 0;
+  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += clips, slot = (slot + 1) % kHostSlots) {
+    const long left = B - r0, done = r0;
+    const long ramp_in = done < clips_per_chunk ? (done < 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
+    const long ramp_out = left <= clips_per_chunk ? (left <= clips_per_chunk / 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
+    long want = ramp_in < ramp_out ? ramp_in : ramp_out;
+    if (want < 1) want = 1;
+    clips = left < want ? left : want;
+    const size_t n = (size_t)clips * clip_samples;
+    cudaStream_t s = ws.st[slot];
+    check(cudaMemcpyAsync(ws.d_x[slot], x_host + (size_t)r0 * clip_samples, n * sizeof(Sample), cudaMemcpyHostToDevice, s));
+    if (rc) break;
+    if constexpr (kPcm) {
+      rc = pqmf_analysis_pcm16(static_cast<const int16_t*>(ws.d_x[slot]), ws.d_y[slot], d_hk, d_tab, (int)clips, T, C, 0, F, M, L, flags, s);
+      if (rc) break;
+      rc = pqmf_synthesis_pcm16(ws.d_y[slot], static_cast<int16_t*>(ws.d_o[slot]), d_hk, d_tab, (int)clips, C, F, M, L, delay_frames, flags, s);
+    } else {
+      rc = pqmf_analysis_f32(static_cast<const float*>(ws.d_x[slot]), ws.d_y[slot], d_hk, d_tab, (int)clips, T, F, M, L, flags, s);
+      if (rc) break;
+      rc = pqmf_synthesis_f32(ws.d_y[slot], static_cast<float*>(ws.d_o[slot]), d_hk, d_tab, (int)clips, F, M, L, delay_frames, flags, s);
+    }
+    if (rc) break;
+    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * clip_samples, ws.d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    check(cudaMemcpyAsync(out_host + (size_t)r0 * clip_samples, ws.d_o[slot], n * sizeof(Sample), cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < kHostSlots; ++i) check(cudaStreamSynchronize(ws.st[i]));
+  return rc;
 }
 
 }  // namespace
@@ -589,6 +676,76 @@ int pqmf_synthesis_f32(const float* s, float* out, const float* hk, const float*
   return synthesis_direct(s, nullptr, out, hk, B, n_frames, M, L, off2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st);
 }
 
+int pqmf_analysis_pcm16(const int16_t* pcm, float* y, const float* hk, const float* tables, int B, long T, int C, int downmix,
+                        long n_frames, int M, int L, unsigned flags, pqmf_stream_t stream) {
+  if (bad_dims(B, T, M, L) || n_frames < 0 || C < 1 || C > 64) return PQMF_ERR_ARG;
+  const long rows = downmix ? (long)B : (long)B * C;
+  if (rows >= (1L << 31)) return PQMF_ERR_ARG;
+  if (B == 0 || n_frames == 0) return PQMF_OK;
+  if (!pcm || !y || !hk) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const pqmf::PcmIn in{pcm, C, downmix ? 1 : 0};
+  if (use_h4_family(M, L, tables, flags) && use_h4((int)rows, n_frames, M, nullptr) && T > 0 && (T % M) == 0 && (T % 8) == 0 && n_frames == T / M &&
+      ((uintptr_t)pcm % 32) == 0 && ((uintptr_t)y % 16) == 0) {
+    const int e = h4_analysis(nullptr, y, tables, (int)rows, T, n_frames, M, L, flags, st, in);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  return analysis_direct(nullptr, nullptr, y, hk, (int)rows, T, n_frames, M, L, L / 2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st, in);
+}
+
+int pqmf_synthesis_pcm16(const float* s, int16_t* pcm, const float* hk, const float* tables, int B, int C, long n_frames, int M, int L,
+                         int delay_frames, unsigned flags, pqmf_stream_t stream) {
+  if (bad_dims(B, n_frames, M, L) || delay_frames < 0 || delay_frames > 1 || C < 1 || C > 64) return PQMF_ERR_ARG;
+  const long rows = (long)B * C;
+  if (rows >= (1L << 31)) return PQMF_ERR_ARG;
+  if (B == 0 || n_frames == 0) return PQMF_OK;
+  if (!s || !pcm || !hk) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int off2 = L / 2 - delay_frames * M;
+  if (use_h4_family(M, L, tables, flags) && use_h4((int)rows, n_frames, M, nullptr) && n_frames > 0 && (n_frames & 3) == 0 && ((uintptr_t)s % 16) == 0 &&
+      ((uintptr_t)pcm % 16) == 0) {
+    const int e = h4_synthesis(s, nullptr, tables, (int)rows, n_frames, off2, M, L, flags, st, pcm, C);
+    if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
+  }
+  return synthesis_direct(s, nullptr, nullptr, hk, (int)rows, n_frames, M, L, off2, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st, pcm, C);
+}
+
+int pqmf_synthesis_bands_f32(const float* const* bands, const long* lens, float* out, const float* hk, int B, long n_frames, int M, int L,
+                             int delay_frames, const float* prev_tail, const float* fade_out, const float* fade_in, float* tail_out, int Lx,
+                             unsigned flags, pqmf_stream_t stream) {
+  if (bad_dims(B, n_frames, M, L) || delay_frames < 0 || delay_frames > 1 || M > pqmf::kMaxBandTable || Lx < 0) return PQMF_ERR_ARG;
+  if (!bands || !lens) return PQMF_ERR_ARG;
+  const bool fade = prev_tail != nullptr && Lx > 0;
+  if (fade && (!fade_out || !fade_in || !tail_out || tail_out == prev_tail)) return PQMF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  pqmf::BandTable t{};
+  t.enabled = 1;
+  t.Lx = Lx;
+  for (int k = 0; k < M; ++k) {
+    if (lens[k] < 0 || lens[k] >= (1L << 31) || (!bands[k] && lens[k] > 0 && B > 0)) return PQMF_ERR_ARG;
+    t.band[k] = bands[k];
+    t.len[k] = (int)lens[k];
+    // centre crop / zero pad to n_frames (1-PitchShifterWrapper.py:279-289): cur > target: start = (cur - target) // 2; else left = pad // 2
+    t.start[k] = lens[k] > n_frames ? (int)((lens[k] - n_frames) / 2) : -(int)((n_frames - lens[k]) / 2);
+  }
+  // the reference cross-fades only for batch 1 (:262); other batch sizes leave the bands and the kept tail as they are
+  if (fade && B == 1) {
+    t.prev_tail = prev_tail;
+    t.fade_out = fade_out;
+    t.fade_in = fade_in;
+    const int n = M * Lx;
+    pqmf::band_tail_kernel<<<(n + 255) / 256, 256, 0, st>>>(t, M, tail_out);
+    ++g_launches;
+    if (int e = cuda_status()) return e;
+  } else if (fade) {
+    cudaError_t e = cudaMemcpyAsync(tail_out, prev_tail, (size_t)M * Lx * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (B == 0 || n_frames == 0) return PQMF_OK;
+  if (!out || !hk) return PQMF_ERR_ARG;
+  return synthesis_direct(nullptr, nullptr, out, hk, B, n_frames, M, L, L / 2 - delay_frames * M, 0, (flags & PQMF_FLAG_NO_SIGN) ? 1 : 0, st, nullptr, 1, &t);
+}
+
 int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const float* tables, const float* state_in,
                              float* state_out, int B, long T, int M, int L, int frame_parity, unsigned flags,
                              pqmf_stream_t stream) {
@@ -643,96 +800,86 @@ int pqmf_roundtrip_f32(const float* x, float* y, float* out, const float* hk, co
   return pqmf_synthesis_f32(y, out, hk, tables, B, n_frames, M, L, delay_frames, flags, stream);
 }
 
+// rows per chunk of pqmf_reconstruct_f32: the chunk's sub-bands (rows * T * 4 bytes) stay in the 126 MB L2 between the analysis and
+// the synthesis launch, and a chunk is large enough for the tensor-core kernels (>= 96 tiles of 8192 samples) whenever the batch is
+long recon_chunk_rows(int B, long T) {
+  const long row_bytes = T * (long)sizeof(float);
+  long rows = (48L << 20) / (row_bytes > 0 ? row_bytes : 1);
+  const long tiles_per_row = (T + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples;
+  const long min_rows = (96 + tiles_per_row - 1) / (tiles_per_row > 0 ? tiles_per_row : 1);
+  if (rows < min_rows) rows = min_rows;
+  if (rows < 1) rows = 1;
+  return rows < B ? rows : B;
+}
+
+size_t pqmf_reconstruct_scratch_bytes(int B, long T, long n_frames, int M) {
+  if (B <= 0 || T <= 0 || n_frames <= 0 || M <= 0) return 0;
+  return (size_t)recon_chunk_rows(B, T) * (size_t)M * (size_t)n_frames * sizeof(float);
+}
+
+int pqmf_reconstruct_f32(const float* x, float* out, float* scratch, size_t scratch_bytes, const float* hk, const float* tables, int B, long T,
+                         long n_frames, int M, int L, int delay_frames, unsigned flags, pqmf_stream_t stream) {
+  if (bad_dims(B, T, M, L) || n_frames < 0 || delay_frames < 0 || delay_frames > 1) return PQMF_ERR_ARG;
+  if (B == 0 || n_frames == 0) return PQMF_OK;
+  if (!x || !out || !hk || !scratch || scratch_bytes < pqmf_reconstruct_scratch_bytes(B, T, n_frames, M)) return PQMF_ERR_ARG;
+  const long rows = recon_chunk_rows(B, T);
+  for (long r0 = 0; r0 < B; r0 += rows) {
+    const int n = (int)(B - r0 < rows ? B - r0 : rows);
+    int e = pqmf_analysis_f32(x + (size_t)r0 * T, scratch, hk, tables, n, T, n_frames, M, L, flags, stream);
+    if (e) return e;
+    e = pqmf_synthesis_f32(scratch, out + (size_t)r0 * M * n_frames, hk, tables, n, n_frames, M, L, delay_frames, flags, stream);
+    if (e) return e;
+  }
+  return PQMF_OK;
+}
+
 int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
                             const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
                             int device) {
+  return roundtrip_host(x_host, y_host, out_host, hk_host, tables_host, B, T, 1, M, L, delay_frames, flags, device);
+}
+
+int pqmf_roundtrip_host_pcm16(const int16_t* pcm_host, float* y_host, int16_t* out_host, const float* hk_host,
+                              const float* tables_host, int B, long T, int C, int M, int L, int delay_frames, unsigned flags,
+                              int device) {
+  if (C < 1 || C > 64) return PQMF_ERR_ARG;
+  return roundtrip_host(pcm_host, y_host, out_host, hk_host, tables_host, B, T, C, M, L, delay_frames, flags, device);
+}
+
+int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
+                                  const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
+                                  const int* devices, int n_devices) {
+  if (!devices || n_devices < 1 || n_devices > kMaxDevices) return PQMF_ERR_ARG;
   if (bad_dims(B, T, M, L) || !x_host || !out_host || !hk_host || (T % M) != 0) return PQMF_ERR_ARG;
-  if (B == 0 || T == 0) return PQMF_OK;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || device >= kMaxDevices) return PQMF_ERR_NO_DEVICE;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return (int)e;
-  const long F = T / M;
-  // Row chunks of ~16 MiB of input: H2D(i+1), the two kernels of chunk i and D2H(i-1) overlap (PCIe is full duplex),
-  // each chunk on its own stream.  The staging buffers live in a per-device workspace that is created on first use
-  // and only ever grows, so steady-state calls do no allocation.
-  static const long chunk_bytes = [] {
-    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 16 MiB of input per chunk
-    const long v = e ? atol(e) : 0;
-    return (v > 0 && v <= 1024 ? v : 16L) << 20;
-  }();
-  long rows_per_chunk = chunk_bytes / (T * (long)sizeof(float));
-  if (rows_per_chunk < 1) rows_per_chunk = 1;
-  if (rows_per_chunk > B) rows_per_chunk = B;
-  const size_t chunk_elems = (size_t)rows_per_chunk * T;
-  const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
-  std::lock_guard<std::mutex> lock(g_host_mutex);
-  HostWorkspace& ws = g_host_ws[device];
-  int rc = PQMF_OK;
-  auto check = [&](cudaError_t err) { if (err != cudaSuccess && rc == PQMF_OK) rc = (int)err; return err == cudaSuccess; };
-  if (!ws.streams_ready) {
-    for (int i = 0; i < kHostSlots; ++i) check(cudaStreamCreateWithFlags(&ws.st[i], cudaStreamNonBlocking));
-    ws.streams_ready = (rc == PQMF_OK);
-  }
-  if (rc == PQMF_OK && ws.chunk_elems < chunk_elems) {
-    for (int i = 0; i < kHostSlots; ++i) {
-      if (ws.d_x[i]) cudaFree(ws.d_x[i]);
-      if (ws.d_y[i]) cudaFree(ws.d_y[i]);
-      if (ws.d_o[i]) cudaFree(ws.d_o[i]);
-      ws.d_x[i] = ws.d_y[i] = ws.d_o[i] = nullptr;
-      check(cudaMalloc(&ws.d_x[i], chunk_elems * sizeof(float)));
-      check(cudaMalloc(&ws.d_y[i], chunk_elems * sizeof(float)));
-      check(cudaMalloc(&ws.d_o[i], chunk_elems * sizeof(float)));
+  if (n_devices == 1) return pqmf_roundtrip_host_f32(x_host, y_host, out_host, hk_host, tables_host, B, T, M, L, delay_frames, flags, devices[0]);
+  // rows are independent: contiguous shards, sizes differing by at most one, one host thread per device, no collective
+  std::vector<std::thread> workers;
+  std::vector<int> rcs((size_t)n_devices, PQMF_OK);
+  const long base = B / n_devices, extra = B % n_devices;
+  long r0 = 0;
+  for (int i = 0; i < n_devices; ++i) {
+    const long rows = base + (i < extra ? 1 : 0);
+    if (rows > 0) {
+      const size_t off = (size_t)r0 * T;
+      workers.emplace_back([=, &rcs] {
+        rcs[(size_t)i] = pqmf_roundtrip_host_f32(x_host + off, y_host ? y_host + off : nullptr, out_host + off, hk_host, tables_host, (int)rows, T, M, L,
+                                                 delay_frames, flags, devices[i]);
+      });
     }
-    ws.chunk_elems = (rc == PQMF_OK) ? chunk_elems : 0;
+    r0 += rows;
   }
-  const size_t bank_elems = (size_t)M * L;
-  if (rc == PQMF_OK && ws.bank_elems < bank_elems + (size_t)n_tab) {
-    if (ws.d_bank) cudaFree(ws.d_bank);
-    ws.d_bank = nullptr;
-    check(cudaMalloc(&ws.d_bank, (bank_elems + (size_t)n_tab) * sizeof(float)));
-    ws.bank_elems = (rc == PQMF_OK) ? bank_elems + (size_t)n_tab : 0;
-  }
-  if (rc != PQMF_OK) return rc;
-  float* d_hk = ws.d_bank;
-  float* d_tab = n_tab ? ws.d_bank + bank_elems : nullptr;
-  // the bank is tiny (<= a few hundred KB): re-send it with every call instead of tracking caller-side changes
-  check(cudaMemcpyAsync(d_hk, hk_host, bank_elems * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
-  if (n_tab) check(cudaMemcpyAsync(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
-  check(cudaStreamSynchronize(ws.st[0]));
-  // Chunk schedule: small chunks at both ends (1, 1, 2 rows-per-chunk/4 ... ) shorten the pipeline fill (nothing overlaps the
-  // first H2D) and drain (nothing overlaps the last D2H); full chunks in between keep the kernels efficient.
-  int slot = 0;
-  long rows = 0;
-  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += rows, slot = (slot + 1) % kHostSlots) {
-    const long left = B - r0, done = r0;
-    long want = rows_per_chunk;
-    const long ramp_in = done < rows_per_chunk ? (done < 2 ? rows_per_chunk / 4 : rows_per_chunk / 2) : rows_per_chunk;
-    const long ramp_out = left <= rows_per_chunk ? (left <= rows_per_chunk / 2 ? rows_per_chunk / 4 : rows_per_chunk / 2) : rows_per_chunk;
-    want = ramp_in < ramp_out ? ramp_in : ramp_out;
-    if (want < 1) want = 1;
-    rows = left < want ? left : want;
-    const size_t n = (size_t)rows * T;
-    cudaStream_t s = ws.st[slot];
-    check(cudaMemcpyAsync(ws.d_x[slot], x_host + (size_t)r0 * T, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (rc) break;
-    rc = pqmf_analysis_f32(ws.d_x[slot], ws.d_y[slot], d_hk, d_tab, (int)rows, T, F, M, L, flags, s);
-    if (rc) break;
-    rc = pqmf_synthesis_f32(ws.d_y[slot], ws.d_o[slot], d_hk, d_tab, (int)rows, F, M, L, delay_frames, flags, s);
-    if (rc) break;
-    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * T, ws.d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    check(cudaMemcpyAsync(out_host + (size_t)r0 * T, ws.d_o[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  }
-  for (int i = 0; i < kHostSlots; ++i) check(cudaStreamSynchronize(ws.st[i]));
-  return rc;
+  for (auto& w : workers) w.join();
+  for (int rc : rcs)
+    if (rc != PQMF_OK) return rc;
+  return PQMF_OK;
 }
 
 void pqmf_host_release(void) {
-  std::lock_guard<std::mutex> lock(g_host_mutex);
   int cur = 0;
   cudaGetDevice(&cur);
   for (int d = 0; d < kMaxDevices; ++d) {
     HostWorkspace& ws = g_host_ws[d];
+    std::lock_guard<std::mutex> lock(ws.mutex);
     if (!ws.streams_ready && !ws.d_bank && !ws.chunk_elems) continue;
     cudaSetDevice(d);
     for (int i = 0; i < kHostSlots; ++i) {
@@ -742,7 +889,14 @@ void pqmf_host_release(void) {
       if (ws.streams_ready && ws.st[i]) cudaStreamDestroy(ws.st[i]);
     }
     if (ws.d_bank) cudaFree(ws.d_bank);
-    ws = HostWorkspace{};
+    for (int i = 0; i < kHostSlots; ++i) {
+      ws.st[i] = nullptr;
+      ws.d_x[i] = ws.d_o[i] = nullptr;
+      ws.d_y[i] = nullptr;
+    }
+    ws.d_bank = nullptr;
+    ws.chunk_elems = ws.bank_elems = 0;
+    ws.streams_ready = false;
   }
   cudaSetDevice(cur);
 }

@@ -55,10 +55,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-// ask the L2 for `bytes` (multiple of 16) at a 16-byte aligned global address; no destination, no completion to wait for
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -102,6 +102,102 @@ std::tuple<at::Tensor, at::Tensor> roundtrip(const at::Tensor& x, const at::Tens
   return {out, y};
 }
 
+// int16 PCM edge: pcm [B, T, C] interleaved WAV frames -> sub-bands [B, Cr * M, n_frames] (Cr = C, or 1 when down-mixing)
+at::Tensor analysis_pcm16(const at::Tensor& pcm, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, bool downmix, int64_t flags) {
+  TORCH_CHECK(pcm.is_cuda(), "pcm must be a CUDA tensor (pqmf_b200 has no CPU fallback)");
+  TORCH_CHECK(pcm.scalar_type() == at::kShort, "pcm must be int16, got ", pcm.scalar_type());
+  TORCH_CHECK(pcm.dim() == 3, "pqmf analysis_pcm16 expects interleaved WAV frames [clips, time, channels], got ", pcm.dim(), " dims");
+  const Bank bank = bank_of(hk, pcm);
+  c10::cuda::CUDAGuard guard(pcm.device());
+  const at::Tensor pc = pcm.contiguous();
+  const int64_t B = pc.size(0), T = pc.size(1), C = pc.size(2), Cr = downmix ? 1 : C;
+  TORCH_CHECK(n_frames >= 0 && B * C < (1LL << 31) && C >= 1 && C <= 64, "bad sizes");
+  at::Tensor y = at::empty({B, Cr * bank.M, n_frames}, pc.options().dtype(at::kFloat));
+  if (y.numel() == 0) return y;
+  check_rc(pqmf_analysis_pcm16(pc.data_ptr<int16_t>(), y.data_ptr<float>(), bank.ptr, tables_ptr(tables, pcm), (int)B, (long)T, (int)C, downmix ? 1 : 0,
+                               (long)n_frames, (int)bank.M, (int)bank.L, (unsigned)flags, (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_analysis_pcm16");
+  return y;
+}
+
+// s [B, C * M, F] -> pcm [B, M * F, C] int16 (round to nearest even, saturating)
+at::Tensor synthesis_pcm16(const at::Tensor& s, const at::Tensor& hk, const at::Tensor& tables, int64_t delay_frames, int64_t flags) {
+  check_f32_cuda(s, "s");
+  TORCH_CHECK(s.dim() == 3, "pqmf synthesis_pcm16 expects [batch, channels * n_band, frames], got ", s.dim(), " dims");
+  const Bank bank = bank_of(hk, s);
+  TORCH_CHECK(s.size(1) % bank.M == 0, "sub-band tensor has ", s.size(1), " channels, expected a multiple of n_band=", bank.M);
+  c10::cuda::CUDAGuard guard(s.device());
+  const at::Tensor sc = s.contiguous();
+  const int64_t B = sc.size(0), C = sc.size(1) / bank.M, F = sc.size(2);
+  TORCH_CHECK(B * C < (1LL << 31) && C >= 1 && C <= 64, "bad sizes");
+  at::Tensor pcm = at::empty({B, bank.M * F, C}, sc.options().dtype(at::kShort));
+  if (pcm.numel() == 0) return pcm;
+  check_rc(pqmf_synthesis_pcm16(sc.data_ptr<float>(), pcm.data_ptr<int16_t>(), bank.ptr, tables_ptr(tables, s), (int)B, (int)C, (long)F, (int)bank.M,
+                                (int)bank.L, (int)delay_frames, (unsigned)flags, (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_synthesis_pcm16");
+  return pcm;
+}
+
+// x [B, C, T] -> out [B, C, M * n_frames] only (pqmf_reconstruct_f32): the sub-bands live in a scratch buffer of one row chunk
+at::Tensor reconstruct(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, int64_t delay_frames, int64_t flags) {
+  check_f32_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 3, "pqmf reconstruct expects [batch, channels, time], got ", x.dim(), " dims");
+  const Bank bank = bank_of(hk, x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const at::Tensor xc = x.contiguous();
+  const int64_t B = xc.size(0) * xc.size(1), T = xc.size(2);
+  TORCH_CHECK(n_frames >= 0 && B < (1LL << 31), "bad sizes");
+  at::Tensor out = at::empty({xc.size(0), xc.size(1), bank.M * n_frames}, xc.options());
+  if (out.numel() == 0) return out;
+  const size_t bytes = pqmf_reconstruct_scratch_bytes((int)B, (long)T, (long)n_frames, (int)bank.M);
+  at::Tensor scratch = at::empty({(int64_t)(bytes / sizeof(float))}, xc.options());
+  check_rc(pqmf_reconstruct_f32(xc.data_ptr<float>(), out.data_ptr<float>(), scratch.data_ptr<float>(), bytes, bank.ptr, tables_ptr(tables, x), (int)B,
+                                (long)T, (long)n_frames, (int)bank.M, (int)bank.L, (int)delay_frames, (unsigned)flags,
+                                (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_reconstruct_f32");
+  return out;
+}
+
+// per-band hand-off (pqmf_synthesis_bands_f32): bands = n_band tensors [B, len_k]; returns (out [B, 1, M n_frames], new tail [M, Lx])
+std::tuple<at::Tensor, at::Tensor> synthesis_bands(at::TensorList bands, const at::Tensor& hk, int64_t n_frames, int64_t delay_frames,
+                                                   const at::Tensor& prev_tail, const at::Tensor& fade_out, const at::Tensor& fade_in, int64_t flags) {
+  const Bank bank = bank_of(hk, hk);
+  TORCH_CHECK((int64_t)bands.size() == bank.M, "expected ", bank.M, " band tensors, got ", bands.size());
+  TORCH_CHECK(bank.M <= 64, "synthesis_bands supports n_band <= 64");
+  c10::cuda::CUDAGuard guard(hk.device());
+  std::vector<at::Tensor> keep;
+  std::vector<const float*> ptrs;
+  std::vector<long> lens;
+  int64_t B = -1;
+  for (const at::Tensor& b : bands) {
+    check_f32_cuda(b, "band");
+    TORCH_CHECK(b.dim() == 2 && b.device() == hk.device(), "every band must be a [batch, time] tensor on the bank's device");
+    TORCH_CHECK(B < 0 || b.size(0) == B, "bands disagree on the batch size");
+    B = b.size(0);
+    keep.push_back(b.contiguous());
+    ptrs.push_back(keep.back().data_ptr<float>());
+    lens.push_back((long)b.size(1));
+  }
+  const int64_t Lx = prev_tail.numel() ? prev_tail.size(-1) : 0;
+  const bool fade = Lx > 0;
+  at::Tensor tail_out = at::empty_like(prev_tail);
+  if (fade) {
+    check_f32_cuda(prev_tail, "prev_tail");
+    check_f32_cuda(fade_out, "fade_out");
+    check_f32_cuda(fade_in, "fade_in");
+    TORCH_CHECK(prev_tail.is_contiguous() && prev_tail.numel() == bank.M * Lx && fade_out.numel() == Lx && fade_in.numel() == Lx &&
+                    fade_out.is_contiguous() && fade_in.is_contiguous(),
+                "prev_tail must be [n_band, Lx] and fade_out / fade_in [Lx] (any leading singleton dims), contiguous");
+  }
+  at::Tensor out = at::empty({B, 1, bank.M * n_frames}, hk.options());
+  check_rc(pqmf_synthesis_bands_f32(ptrs.data(), lens.data(), out.data_ptr<float>(), bank.ptr, (int)B, (long)n_frames, (int)bank.M, (int)bank.L,
+                                    (int)delay_frames, fade ? prev_tail.data_ptr<float>() : nullptr, fade ? fade_out.data_ptr<float>() : nullptr,
+                                    fade ? fade_in.data_ptr<float>() : nullptr, fade ? tail_out.data_ptr<float>() : nullptr, (int)Lx, (unsigned)flags,
+                                    (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_synthesis_bands_f32");
+  return {out, tail_out};
+}
+
 // streaming: state tensors are caller-owned ping-pong buffers; state_out is written in place.
 at::Tensor analysis_stream(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& state_in,
                            at::Tensor state_out, int64_t frame_parity, int64_t flags) {
@@ -282,6 +378,10 @@ TORCH_LIBRARY(pqmf_b200, m) {
       "synthesis_stream(Tensor s, Tensor hk, Tensor tables, Tensor state_in, Tensor(a!) state_out, int frame_parity, int flags) "
       "-> Tensor");
   m.def("roundtrip(Tensor x, Tensor hk, Tensor tables, int n_frames, int delay_frames, int flags) -> (Tensor, Tensor)");
+  m.def("reconstruct(Tensor x, Tensor hk, Tensor tables, int n_frames, int delay_frames, int flags) -> Tensor");
+  m.def("synthesis_bands(Tensor[] bands, Tensor hk, int n_frames, int delay_frames, Tensor prev_tail, Tensor fade_out, Tensor fade_in, int flags) -> (Tensor, Tensor)");
+  m.def("analysis_pcm16(Tensor pcm, Tensor hk, Tensor tables, int n_frames, bool downmix, int flags) -> Tensor");
+  m.def("synthesis_pcm16(Tensor s, Tensor hk, Tensor tables, int delay_frames, int flags) -> Tensor");
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -291,6 +391,10 @@ TORCH_LIBRARY_IMPL(pqmf_b200, CUDA, m) {
   m.impl("analysis_stream", &analysis_stream);
   m.impl("synthesis_stream", &synthesis_stream);
   m.impl("roundtrip", &roundtrip);
+  m.impl("reconstruct", &reconstruct);
+  m.impl("synthesis_bands", &synthesis_bands);
+  m.impl("analysis_pcm16", &analysis_pcm16);
+  m.impl("synthesis_pcm16", &synthesis_pcm16);
 }
 
 // gradients w.r.t. the signal / the sub-bands only (the bank is a registered buffer in the reference, not a parameter)

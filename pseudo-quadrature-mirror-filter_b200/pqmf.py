@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import math
 
-from typing import Tuple
+from typing import List, Tuple
 
 import torch
 import torch.nn as nn
@@ -162,6 +162,60 @@ class PQMF(nn.Module):
         return torch.ops.pqmf_b200.synthesis(x, self.hk, self._tables, 0, self._call_flags(x))
 
     @torch.jit.export
+    def reconstruct(self, x: torch.Tensor) -> torch.Tensor:
+        """``inverse(forward(x))`` when nobody needs the sub-bands -- the ``forward`` of the reference's Pvoc wrapper
+        (``1-PitchShifterWrapper.py:303-316``).  The sub-bands go through an L2-sized scratch buffer chunk by chunk instead of a
+        ``[B, n_band, T / n_band]`` tensor: half the DRAM traffic of ``process`` and no sub-band allocation; the same bits."""
+        if x.dim() != 3:
+            raise RuntimeError("reconstruct expects a 3-D tensor [batch, channels, time]")
+        if self.n_band == 1:
+            return x
+        if torch.is_grad_enabled() and x.requires_grad:
+            return self.inverse(self.forward(x))
+        return torch.ops.pqmf_b200.reconstruct(x, self.hk, self._tables, self._n_frames_of(x.shape[-1]), self._inverse_delay(), self._flags)
+
+    def _n_frames_of(self, t: int) -> int:
+        if self.polyphase and t % self.n_band != 0:
+            raise RuntimeError("polyphase PQMF needs the number of samples to be a multiple of n_band")
+        return t // self.n_band
+
+    @torch.jit.export
+    def forward_pcm16(self, pcm: torch.Tensor, downmix: bool = False) -> torch.Tensor:
+        """Analysis straight from 16-bit PCM: ``pcm`` int16 ``[clips, time, channels]`` (interleaved WAV frames) ->
+        sub-bands ``[clips, channels * n_band, time / n_band]``, bit-identical to ``forward(pcm.transpose(1, 2) / 32768)`` -- what
+        ``torchaudio.load`` + ``forward`` give in the reference's scripts -- with the de-interleave and the conversion fused into the
+        kernel's loads.  ``downmix=True``: one row per clip, the mean over the channels (``2-TestBlocks.py:26-30``)."""
+        if pcm.dim() != 3:
+            raise RuntimeError("forward_pcm16 expects int16 WAV frames [clips, time, channels]")
+        t = pcm.shape[1]
+        if self.polyphase and t % self.n_band != 0:
+            raise RuntimeError("polyphase PQMF needs the number of samples to be a multiple of n_band")
+        return torch.ops.pqmf_b200.analysis_pcm16(pcm, self.hk, self._tables, t // self.n_band, downmix, self._flags)
+
+    @torch.jit.export
+    def inverse_pcm16(self, x: torch.Tensor) -> torch.Tensor:
+        """Synthesis straight to 16-bit PCM: sub-bands ``[clips, channels * n_band, frames]`` -> int16 ``[clips, n_band * frames,
+        channels]`` (interleaved WAV frames), ``clamp(round(inverse(x) * 32768), -32768, 32767)`` with the conversion and the
+        interleave fused into the kernel's stores."""
+        if x.dim() != 3:
+            raise RuntimeError("inverse_pcm16 expects a 3-D tensor [batch, channels * n_band, frames]")
+        return torch.ops.pqmf_b200.synthesis_pcm16(x, self.hk, self._tables, self._inverse_delay(), self._flags)
+
+    def _inverse_delay(self) -> int:
+        return 0
+
+    @torch.jit.export
+    def inverse_bands(self, bands: List[torch.Tensor], n_frames: int, prev_tail: torch.Tensor, fade_out: torch.Tensor,
+                      fade_in: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-band hand-off of the pitch-shifter pipeline (reference ``1-PitchShifterWrapper.py:243-297``) as ONE call:
+        ``bands`` are the ``n_band`` pitch-shifted sub-bands ``[B, len_k]`` (each of its own length); every band's first ``Lx`` samples
+        are cross-faded with ``prev_tail[k]`` (``prev_tail * fade_out + band * fade_in``, batch 1 only, as in the reference), the band
+        is centre-cropped / zero-padded to ``n_frames``, and the bands are synthesised -- all inside the kernel's loads, without the
+        ``cat(dim=1)`` tensor.  Returns ``(signal [B, 1, n_band * n_frames], new prev_tail [n_band, Lx])``.  Pass an empty ``prev_tail``
+        (``numel() == 0``) for no cross-fade."""
+        return torch.ops.pqmf_b200.synthesis_bands(bands, self.hk, n_frames, self._inverse_delay(), prev_tail, fade_out, fade_in, self._flags)
+
+    @torch.jit.export
     def process(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """``(inverse(forward(x)), forward(x))`` -- what the reference's ``PQMFWrapper.process`` computes (PQMFWrapper.py:81-92) --
         in one op (bit-identical to the two calls; the synthesis kernel walks its tiles last-to-first, so the tail of the
@@ -233,6 +287,12 @@ class CachedPQMF(PQMF):
     def script_cache(self):
         self.forward_conv.script_cache()
         self.inverse_conv.script_cache()
+
+    def _inverse_delay(self) -> int:
+        return 1  # CachedPQMF.inverse is PQMF.inverse one frame later (pqmf.py:345-354)
+
+    def _n_frames_of(self, t: int) -> int:
+        return (t + self.n_band - 1) // self.n_band  # the cached analysis accepts ragged lengths: ceil(T / n_band) frames
 
     @torch.jit.export
     def reset_stream(self) -> None:

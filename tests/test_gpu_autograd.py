@@ -80,3 +80,32 @@ def test_no_grad_and_scripted_paths_are_unchanged(pq):
     xe = x.clone().requires_grad_(True)
     mod.inverse(mod(xe)).square().sum().backward()
     assert torch.allclose(xs.grad, xe.grad)
+
+
+@pytest.mark.parametrize("scale", (1e-7, 1e-3, 1.0, 3e5))
+def test_gradients_of_any_magnitude(pq, scale):
+    """gradients have no natural scale (a mean-reduced loss gives 1e-7 per sample; an int-scaled signal 1e5), and
+    the tensor-core kernels carry values as fp16 pairs.  The backward passes normalise by an exact power of two on the device, so
+    relative accuracy must not depend on the magnitude -- on the Hankel path (>= 96 tiles) and on the small-batch paths alike."""
+    from oracle import pqmf_port_torch as P
+
+    for b, t in ((24, 32768), (2, 4096)):
+        torch.manual_seed(b)
+        mod = pq.PQMF(100, 16).cuda()
+        hk64 = mod.hk.double().cpu()
+        x = (0.5 * torch.randn(b, 1, t)).clamp_(-1, 1)
+        w = torch.randn(b, 16, t // 16) * scale            # upstream gradient of the analysis output
+        xg = x.cuda().requires_grad_(True)
+        (mod(xg) * w.cuda()).sum().backward()
+        xr = x.double().requires_grad_(True)
+        (P.analysis_polyphase(xr, hk64) * w.double()).sum().backward()
+        assert torch.isfinite(xg.grad).all()
+        assert (xg.grad.cpu().double() - xr.grad).abs().max().item() <= 2e-5 * scale
+        s = (0.3 * torch.randn(b, 16, t // 16))
+        v = torch.randn(b, 1, t) * scale
+        sg = s.cuda().requires_grad_(True)
+        (mod.inverse(sg) * v.cuda()).sum().backward()
+        sr = s.double().requires_grad_(True)
+        (P.synthesis_polyphase(sr, hk64) * v.double()).sum().backward()
+        assert torch.isfinite(sg.grad).all()
+        assert (sg.grad.cpu().double() - sr.grad).abs().max().item() <= 3e-4 * scale   # gain 16 x 16 bands

@@ -479,3 +479,53 @@ def test_cuda_graph_capture_and_replay(pq):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, mod.inverse(mod(x)))
+
+
+@pytest.mark.parametrize("m,b,t", ((16, 64, 1 << 18), (16, 3, 16 * 1000), (8, 40, 8 * 8192), (32, 5, 32 * 300), (16, 200, 16 * 2048 - 7)))
+def test_reconstruct_without_subbands_equals_process(pq, m, b, t):
+    """reconstruct() = inverse(forward(x)) with the sub-bands in an L2-sized scratch instead of a tensor (the Pvoc wrapper's forward,
+    1-PitchShifterWrapper.py:303-316): the same bits as process()'s reconstruction, for every kernel path and for ragged cached lengths."""
+    torch.manual_seed(m + b)
+    x = (0.5 * torch.randn(b, 1, t, device="cuda")).clamp_(-1, 1)
+    for cls in (pq.PQMF, pq.CachedPQMF):
+        if cls is pq.PQMF and t % m:
+            continue
+        mod = cls(100, m).cuda()
+        want, _ = mod.process(x)
+        assert torch.equal(mod.reconstruct(x), want)
+        assert torch.equal(torch.jit.script(mod).reconstruct(x), want)
+    xg = x[:2].clone().requires_grad_(True)
+    mod.reconstruct(xg).square().sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
+
+
+@pytest.mark.parametrize("scale,tol", ((1e-6, 2e-10), (1e-4, 5e-10), (1e-3, 5e-9), (1.0, 5e-6), (2.0e4, 0.1)))
+def test_quiet_and_loud_signals_keep_relative_accuracy(golden, pq, scale, tol):
+    """Round 2: the second fp16 term is scaled by 2^11, so the tensor-core kernels keep RELATIVE accuracy (TOL / 2 of the signal scale)
+    down to 1e-4 of full scale, and an absolute floor of ~1e-11 per sample below that (it was 3e-8); check_range=True routes anything
+    beyond to plain fp32."""
+    hk = golden("bank_M16.npz")["hk"]
+    b, t = 24, 32768
+    x = (O.audio_like((b, 1, t), 78) * scale).astype(np.float32)
+    mod = pq.PQMF(100, 16).cuda()
+    y = mod(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0].astype(np.float64), hk)
+    assert np.isfinite(y).all() and np.abs(y - y64).max() <= tol
+    s = y64.astype(np.float32)
+    out = mod.inverse(dev(s)).cpu().numpy()
+    assert np.isfinite(out).all() and np.abs(out[:, 0] - O.synthesis(s.astype(np.float64), hk)).max() <= 2 * tol
+
+
+def test_check_range_routes_out_of_range_inputs_to_fp32(golden, pq):
+    hk = golden("bank_M16.npz")["hk"]
+    x = (O.audio_like((24, 1, 32768), 79) * 1.0e5).astype(np.float32)   # beyond the fp16 range of the tensor-core kernels
+    guarded = pq.PQMF(100, 16, check_range=True).cuda()
+    y = guarded(dev(x)).cpu().numpy()
+    y64 = O.analysis(x[:, 0].astype(np.float64), hk)
+    assert np.isfinite(y).all() and np.abs(y - y64).max() <= 1e-5 * 1.0e5
+    plain = pq.PQMF(100, 16, fp32=True).cuda()
+    assert np.array_equal(plain(dev(x)).cpu().numpy(), y)
+    tiny = (O.audio_like((24, 1, 32768), 80) * 1.0e-9).astype(np.float32)
+    yt = guarded(dev(tiny)).cpu().numpy()
+    assert np.abs(yt - O.analysis(tiny[:, 0].astype(np.float64), hk)).max() <= 1e-5 * 1.0e-9
+    assert torch.jit.script(guarded)(dev(x)).shape == (24, 16, 2048)

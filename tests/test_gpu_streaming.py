@@ -134,3 +134,36 @@ def test_config3_sixty_four_steps_equal_offline(pq):
     assert lat == 528
     err = out_s[..., lat:] - x[..., :-lat]
     assert (10 * torch.log10((x[..., :-lat] ** 2).sum() / (err ** 2).sum())).item() > 55.0
+
+
+@pytest.mark.parametrize("streams,block", ((1, 512), (1, 4096), (300, 2048), (5, 16384)))
+def test_stream_graph_replay_equals_eager_streaming(pq, streams, block):
+    """StreamGraph: the block step (forward_stream + inverse_stream) as two alternating CUDA graphs over fixed buffers -- the same
+    bits as the eager calls, block after block, and reset() starts a new stream without re-capturing."""
+    torch.manual_seed(streams + block)
+    n_blocks = 7
+    x = (0.5 * torch.randn(streams, 1, block * n_blocks, device="cuda")).clamp_(-1, 1)
+    eager = pq.CachedPQMF(100, 16).cuda()
+    y_e, out_e = _run_stream(eager, x, block)
+    graph = pq.StreamGraph(pq.CachedPQMF(100, 16).cuda(), streams, block)
+    for rep in range(2):
+        ys, outs = [], []
+        for i in range(n_blocks):
+            y, out = graph.step(x[..., i * block : (i + 1) * block])
+            ys.append(y.clone())
+            outs.append(out.clone())
+        assert torch.equal(torch.cat(ys, -1), y_e) and torch.equal(torch.cat(outs, -1), out_e)
+        graph.reset()
+    with pytest.raises(ValueError):
+        pq.StreamGraph(pq.CachedPQMF(100, 16).cuda(), 1, 48)  # three frames per block: the frame parity would have to alternate
+
+
+def test_stream_ops_refuse_to_be_differentiated(pq):
+    mod = pq.CachedPQMF(100, 16).cuda()
+    x = torch.randn(2, 1, 2048, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="not differentiable"):
+        mod.forward_stream(x)
+    with torch.no_grad():
+        y = mod.forward_stream(x)
+    with pytest.raises(RuntimeError, match="not differentiable"):
+        mod.inverse_stream(y.requires_grad_(True))
