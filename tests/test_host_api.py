@@ -26,11 +26,12 @@ def test_cabi_exports_every_declared_symbol(pq):
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(pqmf_[a-z0-9_]+)\s*\(", header))
     assert {"pqmf_analysis_f32", "pqmf_synthesis_f32", "pqmf_analysis_stream_f32", "pqmf_synthesis_stream_f32",
-            "pqmf_build_tables_f32", "pqmf_roundtrip_host_f32"} <= declared
+            "pqmf_build_tables_f32", "pqmf_roundtrip_host_f32", "pqmf_analysis_pcm16", "pqmf_synthesis_pcm16", "pqmf_synthesis_bands_f32",
+            "pqmf_reconstruct_f32", "pqmf_roundtrip_host_pcm16", "pqmf_roundtrip_host_multi_f32"} <= declared
     lib = ctypes.CDLL(pq.library_paths()[0])
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/pqmf_b200.h but not exported"
-    assert lib.pqmf_abi_version() == 1
+    assert lib.pqmf_abi_version() == 2
 
 
 def test_torch_ops_are_registered_for_cuda_only(pq):
