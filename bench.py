@@ -269,8 +269,34 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = n_gpus * BATCH * N_SAMPLES / (e2e_ms * 1e-3) * 1e-6
+
+    # ---- the same end to end with 16-bit PCM on both sides of the link (the reference's inputs are int16 WAVs): the
+    #      conversion happens inside the kernels' loads / stores, so 2 B/sample cross PCIe each way instead of 4.  A SECOND number,
+    #      reported beside the fp32 headline, never instead of it.
+    hp = (x[:, 0] * 32767.0).round().to(torch.int16).cpu().reshape(BATCH, N_SAMPLES, 1).pin_memory()
+    hop = torch.empty_like(hp).pin_memory()
+
+    def host_step_pcm():
+        rc = _lib.cabi.pqmf_roundtrip_host_pcm16(hp.data_ptr(), None, hop.data_ptr(), hk_h.data_ptr(), tab_h.data_ptr() if tab_h.numel() else None,
+                                                 BATCH, N_SAMPLES, 1, N_BAND, int(hk_h.shape[1]), 0, flags, local_rank)
+        _lib.check(rc, "pqmf_roundtrip_host_pcm16")
+
+    for _ in range(2):
+        host_step_pcm()
+    # near-perfect reconstruction survives the 16-bit quantisation: the output frames sit within a few LSB of the input frames
+    pcm_err = (hop[:4, 4096:-4096, 0].to(torch.int32) - hp[:4, 4096:-4096, 0].to(torch.int32)).abs().float().mean().item()
+    assert pcm_err < 40.0, f"PCM round trip is off by {pcm_err:.1f} LSB on average"
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_step_pcm()
+    pcm_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    pcm_ms = _max_over_ranks(torch, dist, dev, pcm_ms, distributed)
+    pcm_value = n_gpus * BATCH * N_SAMPLES / (pcm_ms * 1e-3) * 1e-6
     _lib.cabi.pqmf_host_release()
-    del hx, ho
+    del hx, ho, hp, hop
 
     peak, peak_src = measured_peak_gbs()
     other = None if args.no_other_configs else other_configs(torch, dist, pq, dev, mod, x, peak, n_gpus, distributed)
@@ -314,6 +340,9 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 4, "d2h_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 4,
                 "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "api": "pqmf_roundtrip_host_f32 (C ABI, pinned host buffers, 16 MiB row chunks on 4 streams)"},
+        "e2e_pcm16": {"value": round(pcm_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 2, "d2h_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 2,
+                      "ms_per_step": round(pcm_ms, 3), "steps": e2e_steps, "api": "pqmf_roundtrip_host_pcm16 (int16 WAV frames in pinned host memory in and out; "
+                      "second number beside the fp32 headline)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

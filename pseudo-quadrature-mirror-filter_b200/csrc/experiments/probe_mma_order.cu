@@ -93,12 +93,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_kernel(con
           const uint64_t db128 = umma_desc(smem_u32(sm + OFF_B128), 1024, 128), db64 = umma_desc(smem_u32(sm + OFF_B64), 512, 128);
           const uint32_t d0 = tm + 128 * (r & 1), d1 = d0 + ((order & 2) ? 64u : 0u);   // order bit 1: the N = 64 pass accumulates into columns 64-127
           auto astep = [&](int s) { return da + (uint64_t)(8 * (s >> 2) + 2 * (s & 3)); };
-          if (order & 1) {   // interleaved: N = 128 (step s), N = 64 (step s), ...
-            const int nmax = n128 > n64 ? n128 : n64;
-            for (int s = 0; s < nmax; ++s) {
-              if (s < n128) umma2_f16(d0, astep(s), db128 + (uint64_t)(128 * s), idesc128, s != 0);
-              if (s < n64) umma2_f16(d1, astep(s), db64 + (uint64_t)(64 * s), idesc64, true);
+          if (order & 1) {   // interleaved, branch-free: N = 128 (step s), N = 64 (step s), ... over the common count; the rest after
+            const int nmin = n128 < n64 ? n128 : n64;
+            for (int s = 0; s < nmin; ++s) {
+              umma2_f16(d0, astep(s), db128 + (uint64_t)(128 * s), idesc128, s != 0);
+              umma2_f16(d1, astep(s), db64 + (uint64_t)(64 * s), idesc64, true);
             }
+            for (int s = nmin; s < n128; ++s) umma2_f16(d0, astep(s), db128 + (uint64_t)(128 * s), idesc128, s != 0);
+            for (int s = nmin; s < n64; ++s) umma2_f16(d1, astep(s), db64 + (uint64_t)(64 * s), idesc64, true);
           } else {
             for (int s = 0; s < n128; ++s) umma2_f16(d0, astep(s), db128 + (uint64_t)(128 * s), idesc128, s != 0);
             for (int s = 0; s < n64; ++s) umma2_f16(d1, astep(s), db64 + (uint64_t)(64 * s), idesc64, true);

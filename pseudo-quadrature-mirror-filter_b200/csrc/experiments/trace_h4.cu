@@ -23,15 +23,15 @@ int main(int argc, char** argv) {
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   H4AnalysisParams p{};
-  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim_lo = p.trim_hi = argc > 3 ? atoi(argv[3]) : 0; p.g = (argc > 6 && atoi(argv[6]) == 2) ? h4_shape(16, 64, 384, pair, false) : h4_shape_deep(16, 64, 384, pair, false); p.no_l2_prefetch = argc > 5 && atoi(argv[5]);
+  p.x = x; p.y = y; p.bank = bank; p.T = T; p.F = F; p.off = 256; p.parity = 0; p.trace = tr; p.trim_lo = p.trim_hi = argc > 3 ? atoi(argv[3]) : 0; p.g = h4_shape(16, 64, 384, pair, false);
   for (int rep = 0; rep < 3; ++rep) {
     int rc = (pair ? h4_launch_analysis<16, true>(p, B, 0) : h4_launch_analysis<16, false>(p, B, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
   }
-  const bool synth = argc > 2 && argv[2][0] == 's';   // trace_h4 <random> <a|s> <trim> <pair> <no_l2_prefetch> <nbuf 2|3>
+  const bool synth = argc > 2 && argv[2][0] == 's';   // trace_h4 <random> <a|s> <trim> <pair>
   H4SynthesisParams q{};
-  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim_lo = q.trim_hi = argc > 3 ? atoi(argv[3]) : 0; q.g = (argc > 6 && atoi(argv[6]) == 2) ? h4_shape(16, 64, 384, pair, true) : h4_shape_deep(16, 64, 384, pair, true); q.no_l2_prefetch = argc > 5 && atoi(argv[5]);
+  q.s = x; q.out = y; q.bank = bank; q.F = F; q.o = 16; q.parity = 0; q.trace = tr; q.trim_lo = q.trim_hi = argc > 3 ? atoi(argv[3]) : 0; q.g = h4_shape(16, 64, 384, pair, true);
   if (synth) {
     cudaMemset(tr, 0, 64 * 64 * 8);
     (pair ? h4_launch_synthesis<16, true>(q, B, 0) : h4_launch_synthesis<16, false>(q, B, 0));
