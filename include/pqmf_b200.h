@@ -150,6 +150,14 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
                               float* state_out, int B, long n_frames, int M, int L, int frame_parity, unsigned flags,
                               pqmf_stream_t stream);
 
+/* ---- one streaming block step: pqmf_analysis_stream_f32 followed by pqmf_synthesis_stream_f32 of the sub-bands it produced (what
+ *      PQMFWrapper.process does per audio buffer in cached mode, PQMFWrapper.py:81-92), as ONE call (two launches on `stream`).
+ *      x [B, T] -> y [B, M, T/M] and out [B, T]; xstate_* [B, L], sstate_* [B, M, L/M] as for the two entry points; parity_in /
+ *      parity_out = global index & 1 of the first analysis frame / of the first sub-band frame fed to the synthesis. ---- */
+int pqmf_stream_step_f32(const float* x, float* y, float* out, const float* hk, const float* tables, const float* xstate_in, float* xstate_out,
+                         const float* sstate_in, float* sstate_out, int B, long T, int M, int L, int parity_in, int parity_out, unsigned flags,
+                         pqmf_stream_t stream);
+
 /* ---- fused round trip on device buffers: PQMFWrapper.process (PQMFWrapper.py:81-92: forward, then inverse of the same
  *      sub-bands) and the Pvoc wrapper's forward (1-PitchShifterWrapper.py:303-316) ----
  * pqmf_analysis_f32 followed by pqmf_synthesis_f32 on the same stream, as one call; the synthesis kernels walk their tiles

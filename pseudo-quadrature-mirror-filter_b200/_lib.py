@@ -80,6 +80,9 @@ cabi.pqmf_synthesis_pcm16.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c
 cabi.pqmf_roundtrip_host_f32.restype = ctypes.c_int
 cabi.pqmf_roundtrip_host_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_uint, ctypes.c_int]
+cabi.pqmf_stream_step_f32.restype = ctypes.c_int
+cabi.pqmf_stream_step_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_uint, _vp]
 cabi.pqmf_synthesis_bands_f32.restype = ctypes.c_int
 cabi.pqmf_synthesis_bands_f32.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp,
                                           ctypes.c_int, ctypes.c_uint, _vp]

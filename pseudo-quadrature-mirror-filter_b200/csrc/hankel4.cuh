@@ -214,9 +214,9 @@ __device__ __forceinline__ void h4_teardown(uint32_t tmem, int warp) {
 // the issuing thread for ~3200 cycles), so this warp does nothing else and the pipe never waits for a converting thread
 template <bool PAIR>
 __device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g, uint32_t tmem, unsigned n_iter, int pad_bytes, int tlo,
-                                               int thi) {
+                                               int thi, unsigned it0 = 0) {
   const uint32_t bank_addr = ptx::smem_u32(s.bank), plane_addr = ptx::smem_u32(s.planes);
-  for (unsigned it = 0; it < n_iter; ++it) {
+  for (unsigned it = it0; it < it0 + n_iter; ++it) {   // it0 > 0: a second phase of the same kernel continues the barrier sequence
     const int pb = (int)(it & 1);
     ptx::mbar_wait(&s.pfull[pb], (it >> 1) & 1);
     ptx::tc_fence_after();
@@ -230,14 +230,15 @@ __device__ __forceinline__ void h4_issuer_loop(const H4Smem& s, const H4Shape& g
   }
 }
 
-// a worker warp publishes its share of planes[pb]: one arrival per warp, after this CTA's bank image has landed
+// a worker warp publishes its share of planes[pb]: one arrival per warp, after this CTA's bank image has landed (the first tile of a
+// phase waits for it: bank_phase = how many images were loaded before this one)
 template <bool PAIR>
-__device__ __forceinline__ void h4_publish(const H4Smem& s, uint32_t pfull_leader, unsigned it, int pb, int tid) {
+__device__ __forceinline__ void h4_publish(const H4Smem& s, uint32_t pfull_leader, unsigned it, int pb, int tid, unsigned it0 = 0, unsigned bank_phase = 0) {
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncwarp();
   if ((tid & 31) == 0) {
-    if (it == 0) ptx::mbar_wait(s.bankfull, 0);
+    if (it == it0) ptx::mbar_wait(s.bankfull, bank_phase & 1);
     if constexpr (PAIR) ptx::mbar_arrive_cluster(pfull_leader + 8u * pb);
     else ptx::mbar_arrive(&s.pfull[pb]);
   }

@@ -37,18 +37,134 @@ struct H4AnalysisStreamParams {
   long T;
   int B, L;
   int parity, trim_lo, trim_hi;
+  int keep;               // y is read back by a later phase of the same kernel: store it without the streaming hint
   H4Shape g;
   H4StreamGeom s;
   long n_tiles;
 };
 
+// the worker warps' part of streaming analysis (warps 0-7): tiles blockIdx.x, + gridDim.x, ...; `it0` / `bank_phase` continue the
+// barrier sequence when this is a phase of the fused block-step kernel
 template <bool PAIR>
-__global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4AnalysisStreamParams p) {
+__device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStreamParams& p, const H4Smem& sm, uint32_t tmem, uint32_t pfull_leader,
+                                                           unsigned n_iter, unsigned it0, unsigned bank_phase, int tid) {
   constexpr int M = 16, FR = 4, HB = 8;
   constexpr int NQ = (kH4Rows * 16 + kH4Workers - 1) / kH4Workers;  // 8 float4 per thread cover the 128 region rows of a tile
+  const H4Shape& g = p.g;
+  const H4StreamGeom& sg = p.s;
+  const int warp = tid >> 5;
+  // rows past the last region are read by MMA rows whose results are never stored: make them finite once
+  for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4Workers)
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
+  // tile-invariant map of this thread's quads: region (stream slot) and offset inside the stream's history / block
+  const int region_quads = sg.pitch * 16, n_quads = sg.spt * region_quads;
+  const long F = p.T / M;
+  int q_slot[NQ], q_off[NQ];  // q_off >= 0: sample offset in the block; -1 - h: sample offset h in the history; slot -1: padding (zeros)
+#pragma unroll
+  for (int r = 0; r < NQ; ++r) {
+    const int u = tid + kH4Workers * r;
+    q_slot[r] = -1;
+    q_off[r] = 0;
+    if (u < n_quads) {
+      const int t = u / region_quads, w = u - t * region_quads, q = w >> 4, col = w & 15;
+      if (q < sg.hrows) {
+        q_slot[r] = t;
+        q_off[r] = -1 - ((p.L - sg.hrows * 64) + q * 64 + 4 * col);
+      } else if (q - sg.hrows < sg.rows_b) {
+        q_slot[r] = t;
+        q_off[r] = (q - sg.hrows) * 64 + 4 * col;
+      }
+    }
+  }
+  float4 xr[NQ];
+  auto load_tile = [&](long tile) {
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) {
+      const long sidx = tile * sg.spt + q_slot[r];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q_slot[r] >= 0 && sidx < p.B)
+        v = ptx::ldg128_na(reinterpret_cast<const float4*>(q_off[r] >= 0 ? p.x + (size_t)sidx * p.T + q_off[r] : p.hist_in + (size_t)sidx * p.L + (-1 - q_off[r])));
+      xr[r] = v;
+    }
+  };
+  // fp32 -> fp16 planes; the threads that hold the last L samples of a block also roll the history (here, where the data is
+  // needed anyway: a store next to the load would make every prefetch wait for its own data)
+  auto convert = [&](int pb, long tile) {
+    unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
+    unsigned char* p2 = p1 + g.plane;
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) {
+      const int u = tid + kH4Workers * r;
+      if (u < n_quads) {
+        uint2 a, bq;
+        split2_f16s(xr[r].x, xr[r].y, a.x, bq.x);
+        split2_f16s(xr[r].z, xr[r].w, a.y, bq.y);
+        const uint32_t o = sw128_offset((uint32_t)u * 8u);
+        *reinterpret_cast<uint2*>(p1 + o) = a;
+        *reinterpret_cast<uint2*>(p2 + o) = bq;
+        const long sidx = tile * sg.spt + q_slot[r];
+        if (q_slot[r] >= 0 && q_off[r] >= p.T - p.L && sidx < p.B)
+          *reinterpret_cast<float4*>(p.hist_out + (size_t)sidx * p.L + (q_off[r] - (p.T - p.L))) = xr[r];
+      }
+    }
+  };
+  // D (TMEM) -> y: MMA row i = region t, row q: block row q (frames 4 q .. 4 q + 3) of stream tile * spt + t when q < rows_b
+  const int i = tid & 127, hb = tid >> 7;
+  const int et = i / sg.pitch, eq = i - et * sg.pitch;
+  const bool e_row = et < sg.spt && eq < sg.rows_b;
+  auto epilogue = [&](long tile, int dbuf) {
+    const long sidx = tile * sg.spt + et;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + HB * hb);
+    uint32_t r0[FR][HB], r1[FR][HB];
+#pragma unroll
+    for (int dl = 0; dl < FR; ++dl) {
+      ptx::tmem_ld8(taddr + dl * M, r0[dl]);
+      ptx::tmem_ld8(taddr + 64 + dl * M, r1[dl]);
+    }
+    ptx::tmem_ld_wait();
+    if (!e_row || sidx >= p.B) return;
+    float* yp = p.y + ((size_t)sidx * M + HB * hb) * F + 4 * eq;
+#pragma unroll
+    for (int kk = 0; kk < HB; ++kk) {
+      float w[FR];
+#pragma unroll
+      for (int dl = 0; dl < FR; ++dl) {
+        const uint32_t flip = (((dl + p.parity) & 1) == 0 && (kk & 1)) ? 0x80000000u : 0u;  // global frame parity = parity of dl + frame_parity
+        w[dl] = __uint_as_float(__float_as_uint(h4_combine(r0[dl][kk], r1[dl][kk])) ^ flip);
+      }
+      // a following phase of the same kernel reads these back: plain stores then (L2-coherent), streaming stores otherwise
+      if (p.keep) *reinterpret_cast<float4*>(yp + (size_t)kk * F) = make_float4(w[0], w[1], w[2], w[3]);
+      else __stcs(reinterpret_cast<float4*>(yp + (size_t)kk * F), make_float4(w[0], w[1], w[2], w[3]));
+    }
+  };
+
+  long tile = blockIdx.x;
+  load_tile(tile);
+  long prev_tile = 0;
+  for (unsigned it = it0; it < it0 + n_iter; ++it) {
+    const int pb = (int)(it & 1);
+    convert(pb, tile);
+    h4_publish<PAIR>(sm, pfull_leader, it, pb, tid, it0, bank_phase);
+    if (it + 1 < it0 + n_iter) load_tile(tile + gridDim.x);
+    if (it > it0) {
+      ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      ptx::tc_fence_after();
+      epilogue(prev_tile, (int)((it - 1) & 1));
+    }
+    prev_tile = tile;
+    tile += gridDim.x;
+  }
+  const unsigned last = it0 + n_iter - 1;
+  ptx::mbar_wait(&sm.mma_bar[last & 1], (last >> 1) & 1);
+  ptx::tc_fence_after();
+  epilogue(prev_tile, (int)(last & 1));
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4AnalysisStreamParams p) {
   extern __shared__ __align__(1024) unsigned char h4as_smem[];
   const H4Shape g = p.g;
-  const H4StreamGeom sg = p.s;
   const H4Smem sm = h4_carve(h4as_smem, g);
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int kMmaWarp = kH4Workers / 32;
@@ -57,113 +173,10 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
   const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(sm.pfull), 0) : 0u;
   const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;
   const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
-
   if (warp == kMmaWarp) {
     if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim_lo, p.trim_hi);
   } else {
-    // rows past the last region are read by MMA rows whose results are never stored: make them finite once
-    for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4Workers)
-#pragma unroll
-      for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
-    // tile-invariant map of this thread's quads: region (stream slot) and offset inside the stream's history / block
-    const int region_quads = sg.pitch * 16, n_quads = sg.spt * region_quads;
-    const long F = p.T / M;
-    int q_slot[NQ], q_off[NQ];  // q_off >= 0: sample offset in the block; -1 - h: sample offset h in the history; slot -1: padding (zeros)
-#pragma unroll
-    for (int r = 0; r < NQ; ++r) {
-      const int u = tid + kH4Workers * r;
-      q_slot[r] = -1;
-      q_off[r] = 0;
-      if (u < n_quads) {
-        const int t = u / region_quads, w = u - t * region_quads, q = w >> 4, col = w & 15;
-        if (q < sg.hrows) {
-          q_slot[r] = t;
-          q_off[r] = -1 - ((p.L - sg.hrows * 64) + q * 64 + 4 * col);
-        } else if (q - sg.hrows < sg.rows_b) {
-          q_slot[r] = t;
-          q_off[r] = (q - sg.hrows) * 64 + 4 * col;
-        }
-      }
-    }
-    float4 xr[NQ];
-    auto load_tile = [&](long tile) {
-#pragma unroll
-      for (int r = 0; r < NQ; ++r) {
-        const long sidx = tile * sg.spt + q_slot[r];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q_slot[r] >= 0 && sidx < p.B)
-          v = ptx::ldg128_na(reinterpret_cast<const float4*>(q_off[r] >= 0 ? p.x + (size_t)sidx * p.T + q_off[r] : p.hist_in + (size_t)sidx * p.L + (-1 - q_off[r])));
-        xr[r] = v;
-      }
-    };
-    // fp32 -> fp16 planes; the threads that hold the last L samples of a block also roll the history (here, where the data is
-    // needed anyway: a store next to the load would make every prefetch wait for its own data)
-    auto convert = [&](int pb, long tile) {
-      unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
-      unsigned char* p2 = p1 + g.plane;
-#pragma unroll
-      for (int r = 0; r < NQ; ++r) {
-        const int u = tid + kH4Workers * r;
-        if (u < n_quads) {
-          uint2 a, bq;
-          split2_f16s(xr[r].x, xr[r].y, a.x, bq.x);
-          split2_f16s(xr[r].z, xr[r].w, a.y, bq.y);
-          const uint32_t o = sw128_offset((uint32_t)u * 8u);
-          *reinterpret_cast<uint2*>(p1 + o) = a;
-          *reinterpret_cast<uint2*>(p2 + o) = bq;
-          const long sidx = tile * sg.spt + q_slot[r];
-          if (q_slot[r] >= 0 && q_off[r] >= p.T - p.L && sidx < p.B)
-            *reinterpret_cast<float4*>(p.hist_out + (size_t)sidx * p.L + (q_off[r] - (p.T - p.L))) = xr[r];
-        }
-      }
-    };
-    // D (TMEM) -> y: MMA row i = region t, row q: block row q (frames 4 q .. 4 q + 3) of stream tile * spt + t when q < rows_b
-    const int i = tid & 127, hb = tid >> 7;
-    const int et = i / sg.pitch, eq = i - et * sg.pitch;
-    const bool e_row = et < sg.spt && eq < sg.rows_b;
-    auto epilogue = [&](long tile, int dbuf) {
-      const long sidx = tile * sg.spt + et;
-      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + HB * hb);
-      uint32_t r0[FR][HB], r1[FR][HB];
-#pragma unroll
-      for (int dl = 0; dl < FR; ++dl) {
-        ptx::tmem_ld8(taddr + dl * M, r0[dl]);
-        ptx::tmem_ld8(taddr + 64 + dl * M, r1[dl]);
-      }
-      ptx::tmem_ld_wait();
-      if (!e_row || sidx >= p.B) return;
-      float* yp = p.y + ((size_t)sidx * M + HB * hb) * F + 4 * eq;
-#pragma unroll
-      for (int kk = 0; kk < HB; ++kk) {
-        float w[FR];
-#pragma unroll
-        for (int dl = 0; dl < FR; ++dl) {
-          const uint32_t flip = (((dl + p.parity) & 1) == 0 && (kk & 1)) ? 0x80000000u : 0u;  // global frame parity = parity of dl + frame_parity
-          w[dl] = __uint_as_float(__float_as_uint(h4_combine(r0[dl][kk], r1[dl][kk])) ^ flip);
-        }
-        __stcs(reinterpret_cast<float4*>(yp + (size_t)kk * F), make_float4(w[0], w[1], w[2], w[3]));
-      }
-    };
-
-    long tile = blockIdx.x;
-    load_tile(tile);
-    long prev_tile = 0;
-    for (unsigned it = 0; it < n_iter; ++it) {
-      const int pb = (int)(it & 1);
-      convert(pb, tile);
-      h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
-      if (it + 1 < n_iter) load_tile(tile + gridDim.x);
-      if (it > 0) {
-        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-        ptx::tc_fence_after();
-        epilogue(prev_tile, (int)((it - 1) & 1));
-      }
-      prev_tile = tile;
-      tile += gridDim.x;
-    }
-    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-    ptx::tc_fence_after();
-    epilogue(prev_tile, (int)((n_iter - 1) & 1));
+    h4_analysis_stream_workers<PAIR>(p, sm, tmem, pfull_leader, n_iter, 0, 0, tid);
   }
   h4_teardown<PAIR>(tmem, warp);
 }
@@ -182,12 +195,141 @@ struct H4SynthesisStreamParams {
   long n_tiles;
 };
 
+// the worker warps' part of streaming synthesis (warps 0-8).  OWN: the sub-bands were written by an earlier phase of this kernel
+// (by this very CTA: same tile -> stream map), so they are read through L2 instead of the non-coherent path.
+template <bool PAIR, bool OWN>
+__device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStreamParams& p, const H4Smem& sm, uint32_t tmem, uint32_t pfull_leader,
+                                                            unsigned n_iter, unsigned it0, unsigned bank_phase, int tid) {
+  constexpr int M = 16;
+  const H4Shape& g = p.g;
+  const H4StreamGeom& sg = p.sg;
+  const int warp = tid >> 5;
+  for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4SynWorkers)
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
+  // item (frame quad wq of the tile, band group bg): one plane row = one frame quad at n_band 16
+  const int n_fq = sg.spt * sg.pitch;
+  const int bg = tid / n_fq, wq = tid - bg * n_fq;
+  const bool has_item = tid < 2 * n_fq;
+  const int lt = wq / sg.pitch, lq = wq - lt * sg.pitch;  // region, row within the region
+  float4 v[8];
+  auto load_tile = [&](long tile) {
+    const long sidx = tile * sg.spt + lt;
+    const bool live = has_item && sidx < p.B;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      const size_t band = (size_t)sidx * M + 8 * bg + kk;
+      if (live) {
+        if (lq < sg.hrows) {
+          t = ptx::ldg128_na(reinterpret_cast<const float4*>(p.state_in + band * p.K + (p.K - 4 * sg.hrows) + 4 * lq));
+        } else if (lq - sg.hrows < sg.rows_b) {
+          const float4* src = reinterpret_cast<const float4*>(p.s + band * p.F + 4 * (lq - sg.hrows));
+          t = OWN ? ptx::ldg128_cg(src) : ptx::ldg128_na(src);
+        }
+      }
+      v[kk] = t;
+    }
+  };
+  // sigma(k, n): odd bands flip on even global frames; regions and history lengths are multiples of 4 frames, so the parity is j's
+  const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
+  const int fb = 4 * (lq - sg.hrows);  // first frame of this thread's quad within the block (negative: history)
+  auto convert = [&](int pb, long tile) {
+    if (!has_item) return;
+    unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
+    const long sidx = tile * sg.spt + lt;
+    if (fb >= p.F - p.K && lq - sg.hrows < sg.rows_b && sidx < p.B) {  // the last K frames of the block become the next history
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        *reinterpret_cast<float4*>(p.state_out + ((size_t)sidx * M + 8 * bg + kk) * p.K + (fb - (p.F - p.K))) = v[kk];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t fl = (j & 1) ? flip_odd : flip_even;
+      float w[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const float t = j == 0 ? v[kk].x : j == 1 ? v[kk].y : j == 2 ? v[kk].z : v[kk].w;
+        w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
+      }
+      uint4 h1, h2;
+      split2_f16s(w[0], w[1], h1.x, h2.x);
+      split2_f16s(w[2], w[3], h1.y, h2.y);
+      split2_f16s(w[4], w[5], h1.z, h2.z);
+      split2_f16s(w[6], w[7], h1.w, h2.w);
+      const uint32_t o = sw128_offset((uint32_t)(4 * wq + j) * 32u + 16u * bg);
+      *reinterpret_cast<uint4*>(p1 + o) = h1;
+      *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
+    }
+  };
+  // D (TMEM) -> out, with the 4 x 4 chunk transpose of the offline kernel.  pitch and rows_b are multiples of 4, so the four rows
+  // of a lane quad belong to one region and are valid or not together.
+  const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
+  const int i0 = i & ~3, et = i0 / sg.pitch, eq0 = i0 - et * sg.pitch;
+  const bool e_rows = et < sg.spt && eq0 < sg.rows_b;
+  auto epilogue = [&](long tile, int dbuf) {
+    const long sidx = tile * sg.spt + et;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
+    uint32_t r0[2][16], r1[2][16];
+    ptx::tmem_ld16(taddr, r0[0]);
+    ptx::tmem_ld16(taddr + 64, r1[0]);
+    ptx::tmem_ld16(taddr + 16, r0[1]);
+    ptx::tmem_ld16(taddr + 80, r1[1]);
+    ptx::tmem_ld_wait();
+    float val[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) val[q][e] = h4_combine(r0[q >> 1][8 * (q & 1) + e], r1[q >> 1][8 * (q & 1) + e]);
+    const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float recv = __shfl_xor_sync(0xffffffffu, b0 ? val[2 * pr][e] : val[2 * pr + 1][e], 1);
+        val[2 * pr + 1][e] = b0 ? val[2 * pr + 1][e] : recv;
+        val[2 * pr][e] = b0 ? recv : val[2 * pr][e];
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float recv = __shfl_xor_sync(0xffffffffu, b1 ? val[u][e] : val[u + 2][e], 2);
+        val[u + 2][e] = b1 ? val[u + 2][e] : recv;
+        val[u][e] = b1 ? recv : val[u][e];
+      }
+    if (!e_rows || sidx >= p.B) return;
+    float* op = p.out + (size_t)sidx * (p.F * M) + 64 * eq0 + 32 * hb + 8 * (lane & 3);  // slot q: row eq0 + q of the block
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
+  };
+
+  long tile = blockIdx.x;
+  load_tile(tile);
+  long prev_tile = 0;
+  for (unsigned it = it0; it < it0 + n_iter; ++it) {
+    const int pb = (int)(it & 1);
+    convert(pb, tile);
+    h4_publish<PAIR>(sm, pfull_leader, it, pb, tid, it0, bank_phase);
+    if (it + 1 < it0 + n_iter) load_tile(tile + gridDim.x);
+    if (it > it0) {
+      ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      ptx::tc_fence_after();
+      if (warp < 8) epilogue(prev_tile, (int)((it - 1) & 1));
+    }
+    prev_tile = tile;
+    tile += gridDim.x;
+  }
+  const unsigned last = it0 + n_iter - 1;
+  ptx::mbar_wait(&sm.mma_bar[last & 1], (last >> 1) & 1);
+  ptx::tc_fence_after();
+  if (warp < 8) epilogue(prev_tile, (int)(last & 1));
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H4SynthesisStreamParams p) {
-  constexpr int M = 16;
   extern __shared__ __align__(1024) unsigned char h4ss_smem[];
   const H4Shape g = p.g;
-  const H4StreamGeom sg = p.sg;
   const H4Smem sm = h4_carve(h4ss_smem, g);
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int kMmaWarp = kH4SynWorkers / 32;
@@ -196,128 +338,10 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
   const uint32_t pfull_leader = PAIR ? ptx::mapa_shared(ptx::smem_u32(sm.pfull), 0) : 0u;
   const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;
   const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
-
   if (warp == kMmaWarp) {
     if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim_lo, p.trim_hi);  // (o - ehi) is a multiple of 4 here: no alignment pad
   } else {
-    for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4SynWorkers)
-#pragma unroll
-      for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
-    // item (frame quad wq of the tile, band group bg): one plane row = one frame quad at n_band 16
-    const int n_fq = sg.spt * sg.pitch;
-    const int bg = tid / n_fq, wq = tid - bg * n_fq;
-    const bool has_item = tid < 2 * n_fq;
-    const int lt = wq / sg.pitch, lq = wq - lt * sg.pitch;  // region, row within the region
-    float4 v[8];
-    auto load_tile = [&](long tile) {
-      const long sidx = tile * sg.spt + lt;
-      const bool live = has_item && sidx < p.B;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        const size_t band = (size_t)sidx * M + 8 * bg + kk;
-        if (live) {
-          if (lq < sg.hrows) {
-            t = ptx::ldg128_na(reinterpret_cast<const float4*>(p.state_in + band * p.K + (p.K - 4 * sg.hrows) + 4 * lq));
-          } else if (lq - sg.hrows < sg.rows_b) {
-            t = ptx::ldg128_na(reinterpret_cast<const float4*>(p.s + band * p.F + 4 * (lq - sg.hrows)));
-          }
-        }
-        v[kk] = t;
-      }
-    };
-    // sigma(k, n): odd bands flip on even global frames; regions and history lengths are multiples of 4 frames, so the parity is j's
-    const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
-    const int fb = 4 * (lq - sg.hrows);  // first frame of this thread's quad within the block (negative: history)
-    auto convert = [&](int pb, long tile) {
-      if (!has_item) return;
-      unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
-      const long sidx = tile * sg.spt + lt;
-      if (fb >= p.F - p.K && lq - sg.hrows < sg.rows_b && sidx < p.B) {  // the last K frames of the block become the next history
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          *reinterpret_cast<float4*>(p.state_out + ((size_t)sidx * M + 8 * bg + kk) * p.K + (fb - (p.F - p.K))) = v[kk];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t fl = (j & 1) ? flip_odd : flip_even;
-        float w[8];
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const float t = j == 0 ? v[kk].x : j == 1 ? v[kk].y : j == 2 ? v[kk].z : v[kk].w;
-          w[kk] = (kk & 1) ? __uint_as_float(__float_as_uint(t) ^ fl) : t;
-        }
-        uint4 h1, h2;
-        split2_f16s(w[0], w[1], h1.x, h2.x);
-        split2_f16s(w[2], w[3], h1.y, h2.y);
-        split2_f16s(w[4], w[5], h1.z, h2.z);
-        split2_f16s(w[6], w[7], h1.w, h2.w);
-        const uint32_t o = sw128_offset((uint32_t)(4 * wq + j) * 32u + 16u * bg);
-        *reinterpret_cast<uint4*>(p1 + o) = h1;
-        *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
-      }
-    };
-    // D (TMEM) -> out, with the 4 x 4 chunk transpose of the offline kernel.  pitch and rows_b are multiples of 4, so the four rows
-    // of a lane quad belong to one region and are valid or not together.
-    const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
-    const int i0 = i & ~3, et = i0 / sg.pitch, eq0 = i0 - et * sg.pitch;
-    const bool e_rows = et < sg.spt && eq0 < sg.rows_b;
-    auto epilogue = [&](long tile, int dbuf) {
-      const long sidx = tile * sg.spt + et;
-      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
-      uint32_t r0[2][16], r1[2][16];
-      ptx::tmem_ld16(taddr, r0[0]);
-      ptx::tmem_ld16(taddr + 64, r1[0]);
-      ptx::tmem_ld16(taddr + 16, r0[1]);
-      ptx::tmem_ld16(taddr + 80, r1[1]);
-      ptx::tmem_ld_wait();
-      float val[4][8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) val[q][e] = h4_combine(r0[q >> 1][8 * (q & 1) + e], r1[q >> 1][8 * (q & 1) + e]);
-      const bool b0 = lane & 1, b1 = lane & 2;
-#pragma unroll
-      for (int pr = 0; pr < 2; ++pr)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float recv = __shfl_xor_sync(0xffffffffu, b0 ? val[2 * pr][e] : val[2 * pr + 1][e], 1);
-          val[2 * pr + 1][e] = b0 ? val[2 * pr + 1][e] : recv;
-          val[2 * pr][e] = b0 ? recv : val[2 * pr][e];
-        }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float recv = __shfl_xor_sync(0xffffffffu, b1 ? val[u][e] : val[u + 2][e], 2);
-          val[u + 2][e] = b1 ? val[u + 2][e] : recv;
-          val[u][e] = b1 ? recv : val[u][e];
-        }
-      if (!e_rows || sidx >= p.B) return;
-      float* op = p.out + (size_t)sidx * (p.F * M) + 64 * eq0 + 32 * hb + 8 * (lane & 3);  // slot q: row eq0 + q of the block
-#pragma unroll
-      for (int q = 0; q < 4; ++q) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
-    };
-
-    long tile = blockIdx.x;
-    load_tile(tile);
-    long prev_tile = 0;
-    for (unsigned it = 0; it < n_iter; ++it) {
-      const int pb = (int)(it & 1);
-      convert(pb, tile);
-      h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
-      if (it + 1 < n_iter) load_tile(tile + gridDim.x);
-      if (it > 0) {
-        ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-        ptx::tc_fence_after();
-        if (warp < 8) epilogue(prev_tile, (int)((it - 1) & 1));
-      }
-      prev_tile = tile;
-      tile += gridDim.x;
-    }
-    ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
-    ptx::tc_fence_after();
-    if (warp < 8) epilogue(prev_tile, (int)((n_iter - 1) & 1));
+    h4_synthesis_stream_workers<PAIR, false>(p, sm, tmem, pfull_leader, n_iter, 0, 0, tid);
   }
   h4_teardown<PAIR>(tmem, warp);
 }

@@ -786,6 +786,20 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
   return roll_history(state_in, s, state_out, (long)B * M, K, n_frames, st);
 }
 
+int pqmf_stream_step_f32(const float* x, float* y, float* out, const float* hk, const float* tables, const float* xstate_in, float* xstate_out,
+                         const float* sstate_in, float* sstate_out, int B, long T, int M, int L, int parity_in, int parity_out, unsigned flags,
+                         pqmf_stream_t stream) {
+  if (bad_dims(B, T, M, L) || (T % M) != 0 || T == 0) return PQMF_ERR_ARG;
+  if (B == 0) return PQMF_OK;
+  if (!x || !y || !out || !hk || !xstate_in || !xstate_out || !sstate_in || !sstate_out || xstate_in == xstate_out || sstate_in == sstate_out)
+    return PQMF_ERR_ARG;
+  // Two launches on the same stream.  (One persistent kernel for both phases was built and measured: bit-identical and no faster,
+  // experiments/fused_stream_step.cuh.txt -- the launches are not what a block step costs.)
+  int e = pqmf_analysis_stream_f32(x, y, hk, tables, xstate_in, xstate_out, B, T, M, L, parity_in, flags, stream);
+  if (e) return e;
+  return pqmf_synthesis_stream_f32(y, out, hk, tables, sstate_in, sstate_out, B, T / M, M, L, parity_out, flags, stream);
+}
+
 int pqmf_roundtrip_f32(const float* x, float* y, float* out, const float* hk, const float* tables, int B, long T, long n_frames,
                        int M, int L, int delay_frames, unsigned flags, pqmf_stream_t stream) {
   if (bad_dims(B, T, M, L) || n_frames < 0 || delay_frames < 0 || delay_frames > 1) return PQMF_ERR_ARG;

@@ -250,6 +250,32 @@ at::Tensor synthesis_stream(const at::Tensor& s, const at::Tensor& hk, const at:
   return out;
 }
 
+// one streaming block step: (out, y) = (synthesis_stream(analysis_stream(x)), analysis_stream(x)), both states rolled
+std::tuple<at::Tensor, at::Tensor> stream_step(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& xs_in,
+                                               at::Tensor xs_out, const at::Tensor& ss_in, at::Tensor ss_out, int64_t parity_in, int64_t parity_out,
+                                               int64_t flags) {
+  check_f32_cuda(x, "x");
+  const at::Tensor* states[4] = {&xs_in, &xs_out, &ss_in, &ss_out};
+  for (const at::Tensor* t : states) check_f32_cuda(*t, "state");
+  TORCH_CHECK(x.dim() == 3, "pqmf stream_step expects [streams, channels, block], got ", x.dim(), " dims");
+  const Bank bank = bank_of(hk, x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const at::Tensor xc = x.contiguous();
+  const int64_t B = xc.size(0) * xc.size(1), T = xc.size(2);
+  TORCH_CHECK(T > 0 && T % bank.M == 0, "streaming block length ", T, " must be a positive multiple of n_band=", bank.M);
+  for (const at::Tensor* t : states)
+    TORCH_CHECK(t->is_contiguous() && t->numel() == B * bank.L, "streaming state buffers must be contiguous with ", B * bank.L, " elements");
+  TORCH_CHECK(xs_in.data_ptr() != xs_out.data_ptr() && ss_in.data_ptr() != ss_out.data_ptr(), "state_in and state_out must not alias");
+  at::Tensor y = at::empty({xc.size(0), xc.size(1) * bank.M, T / bank.M}, xc.options());
+  at::Tensor out = at::empty({xc.size(0), xc.size(1), T}, xc.options());
+  if (B == 0) return {out, y};
+  check_rc(pqmf_stream_step_f32(xc.data_ptr<float>(), y.data_ptr<float>(), out.data_ptr<float>(), bank.ptr, tables_ptr(tables, x), xs_in.data_ptr<float>(),
+                                xs_out.data_ptr<float>(), ss_in.data_ptr<float>(), ss_out.data_ptr<float>(), (int)B, (long)T, (int)bank.M, (int)bank.L,
+                                (int)(parity_in & 1), (int)(parity_out & 1), (unsigned)flags, (pqmf_stream_t)at::cuda::getCurrentCUDAStream().stream()),
+           "pqmf_stream_step_f32");
+  return {out, y};
+}
+
 int64_t launch_count() { return (int64_t)pqmf_launch_count(); }
 
 // ---- autograd (the reference path is differentiable, upstream users train through PQMF) --------------------
@@ -378,6 +404,9 @@ TORCH_LIBRARY(pqmf_b200, m) {
       "synthesis_stream(Tensor s, Tensor hk, Tensor tables, Tensor state_in, Tensor(a!) state_out, int frame_parity, int flags) "
       "-> Tensor");
   m.def("roundtrip(Tensor x, Tensor hk, Tensor tables, int n_frames, int delay_frames, int flags) -> (Tensor, Tensor)");
+  m.def(
+      "stream_step(Tensor x, Tensor hk, Tensor tables, Tensor xs_in, Tensor(a!) xs_out, Tensor ss_in, Tensor(b!) ss_out, int parity_in, int parity_out, "
+      "int flags) -> (Tensor, Tensor)");
   m.def("reconstruct(Tensor x, Tensor hk, Tensor tables, int n_frames, int delay_frames, int flags) -> Tensor");
   m.def("synthesis_bands(Tensor[] bands, Tensor hk, int n_frames, int delay_frames, Tensor prev_tail, Tensor fade_out, Tensor fade_in, int flags) -> (Tensor, Tensor)");
   m.def("analysis_pcm16(Tensor pcm, Tensor hk, Tensor tables, int n_frames, bool downmix, int flags) -> Tensor");
@@ -391,6 +420,7 @@ TORCH_LIBRARY_IMPL(pqmf_b200, CUDA, m) {
   m.impl("analysis_stream", &analysis_stream);
   m.impl("synthesis_stream", &synthesis_stream);
   m.impl("roundtrip", &roundtrip);
+  m.impl("stream_step", &stream_step);
   m.impl("reconstruct", &reconstruct);
   m.impl("synthesis_bands", &synthesis_bands);
   m.impl("analysis_pcm16", &analysis_pcm16);

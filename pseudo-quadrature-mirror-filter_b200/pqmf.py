@@ -339,6 +339,33 @@ class CachedPQMF(PQMF):
         return torch.ops.pqmf_b200.roundtrip(x, self.hk, self._tables, n_frames, 1, self._flags)
 
     @torch.jit.export
+    def process_stream(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One streaming block step -- ``y = forward_stream(x); out = inverse_stream(y)`` -- as ONE op call (what ``PQMFWrapper.process``
+        does per audio buffer; half the host-side dispatch of the two calls).  Returns ``(out, y)``; the same bits and the same state
+        updates as the two calls."""
+        rows = x.shape[0] * x.shape[1]
+        length = self.hk.shape[1]
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("pqmf_b200 streaming ops are not differentiable (streaming mode carries state across calls); use forward() / "
+                               "inverse() for training or wrap the call in torch.no_grad()")
+        if self._x_state.shape[1] != rows or self._x_state.device != x.device:
+            self._x_state = torch.zeros(2, rows, length, device=x.device)
+            self._x_slot = 0
+            self._frames_in = 0
+        if self._s_state.shape[1] != rows or self._s_state.device != x.device:
+            self._s_state = torch.zeros(2, rows, length, device=x.device)
+            self._s_slot = 0
+            self._frames_out = 0
+        out, y = torch.ops.pqmf_b200.stream_step(x, self.hk, self._tables, self._x_state[self._x_slot], self._x_state[1 - self._x_slot],
+                                                 self._s_state[self._s_slot], self._s_state[1 - self._s_slot], self._frames_in % 2,
+                                                 self._frames_out % 2, self._flags)
+        self._x_slot = 1 - self._x_slot
+        self._s_slot = 1 - self._s_slot
+        self._frames_in += x.shape[-1] // self.n_band
+        self._frames_out += x.shape[-1] // self.n_band
+        return out, y
+
+    @torch.jit.export
     def forward_stream(self, x: torch.Tensor) -> torch.Tensor:
         """One block of streaming analysis: x [S, 1, T_block] -> [S, n_band, T_block / n_band]; updates state."""
         rows = x.shape[0] * x.shape[1]

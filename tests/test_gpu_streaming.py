@@ -167,3 +167,31 @@ def test_stream_ops_refuse_to_be_differentiated(pq):
         y = mod.forward_stream(x)
     with pytest.raises(RuntimeError, match="not differentiable"):
         mod.inverse_stream(y.requires_grad_(True))
+
+
+@pytest.mark.parametrize("streams,block", ((300, 2048), (4096, 2048), (1000, 512), (97, 7680), (7, 2048), (1, 512)))
+def test_fused_block_step_equals_the_two_calls(pq, streams, block):
+    """process_stream(x) = (inverse_stream(forward_stream(x)), forward_stream(x)) as ONE op call (pqmf_stream_step_f32): the same bits
+    and the same carried state as the two calls, block after block, on every streaming kernel family."""
+    torch.manual_seed(streams + block)
+    n_blocks = 5
+    x = (0.5 * torch.randn(streams, 1, block * n_blocks, device="cuda")).clamp_(-1, 1)
+    two = pq.CachedPQMF(100, 16).cuda()
+    y_e, out_e = _run_stream(two, x, block)
+    one = pq.CachedPQMF(100, 16).cuda()
+    scripted = torch.jit.script(pq.CachedPQMF(100, 16).cuda())
+    for mod in (one, scripted):
+        ys, outs = [], []
+        for i in range(n_blocks):
+            out, y = mod.process_stream(x[..., i * block : (i + 1) * block].contiguous())
+            ys.append(y)
+            outs.append(out)
+        assert torch.equal(torch.cat(ys, -1), y_e)
+        assert torch.equal(torch.cat(outs, -1), out_e)
+    assert torch.equal(one._x_state[one._x_slot], two._x_state[two._x_slot]) and torch.equal(one._s_state[one._s_slot], two._s_state[two._s_slot])
+    # mixing the fused step with the separate calls keeps one consistent stream
+    one.reset_stream()
+    o0, y0 = one.process_stream(x[..., :block].contiguous())
+    y1 = one.forward_stream(x[..., block : 2 * block].contiguous())
+    o1 = one.inverse_stream(y1)
+    assert torch.equal(torch.cat([y0, y1], -1), y_e[..., : 2 * block // 16]) and torch.equal(torch.cat([o0, o1], -1), out_e[..., : 2 * block])
