@@ -454,7 +454,7 @@ def bench_config5(torch, pq, dev, seconds):
 
 def bench_single_stream_latency(torch, pq, dev):
     """The reference's real-time use (PQMFWrapper.py:40-41: one stream, host blocks of 512 ... 16384 samples): microseconds per block
-    step (forward_stream + inverse_stream, state carried) -- eager module calls, wall clock including the host side of every call,
+    step (process_stream = forward_stream + inverse_stream, state carried) -- eager module calls, wall clock including the host side of every call,
     and CUDA-graph replay (pq.StreamGraph) -- next to the real-time budget of the block at 44.1 kHz."""
     out = {}
     for block in (512, 2048, 8192, 16384):
@@ -463,11 +463,11 @@ def bench_single_stream_latency(torch, pq, dev):
         n = 200
         with torch.no_grad():
             for _ in range(10):
-                mod.inverse_stream(mod.forward_stream(xb))
+                mod.process_stream(xb)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(n):
-                mod.inverse_stream(mod.forward_stream(xb))
+                mod.process_stream(xb)
             torch.cuda.synchronize()
             eager_us = (time.perf_counter() - t0) / n * 1e6
             g = pq.StreamGraph(pq.CachedPQMF(ATTEN, N_BAND).to(dev), 1, block)

@@ -50,6 +50,7 @@ struct AnalysisDirectParams {
   int xstride;   // row stride (floats) of the polyphase x tile, odd
   int m_shift;   // log2(M) when M is a power of two, else -1
   PcmIn in;      // in.pcm != nullptr: the rows come from interleaved int16 PCM instead of x
+  float* hist_out;  // streaming: the last L samples of (hist ++ x) per row (must not alias hist); the CTA of a row's last frame tile writes them
 };
 
 template <int BG, int RF>
@@ -125,6 +126,12 @@ __global__ void __launch_bounds__(kDirectThreads) analysis_direct_kernel(Analysi
           acc[r][3] = fmaf(hv.w, xv, acc[r][3]);
         }
       }
+    }
+  }
+  if (p.hist_out != nullptr && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) {  // streaming: roll this row's history (no extra launch)
+    for (int i = tid; i < L; i += kDirectThreads) {
+      const long src = (long)i + p.T - L;  // position in the block; negative: still inside the old history
+      p.hist_out[(size_t)b * L + i] = src >= 0 ? __ldg(xrow + src) : (hrow != nullptr ? __ldg(hrow + i + p.T) : 0.f);
     }
   }
   float* yb = p.y + (size_t)b * M * p.n_frames;
@@ -204,6 +211,7 @@ struct SynthesisDirectParams {
   int16_t* pcm_out;   // != nullptr: write interleaved int16 PCM [clips, M F, C] (row = clip * C + channel) instead of out
   int C;
   BandTable bands;    // bands.enabled: the sub-bands come from n_band separate tensors (s unused)
+  float* hist_out;    // streaming: the last K frames of (hist ++ s) per band row (must not alias hist), written by the row's last frame tile
 };
 
 constexpr int kSynthBandsPerChunk = 4;
@@ -287,6 +295,13 @@ __global__ void __launch_bounds__(kDirectThreads) synthesis_direct_kernel(Synthe
       }
     }
   }
+  if (p.hist_out != nullptr && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) {  // streaming: roll the sub-band history of this row
+    for (int e = tid; e < M * p.K; e += kDirectThreads) {
+      const int k = e / p.K, i = e - k * p.K;
+      const long src = (long)i + p.F - p.K;
+      p.hist_out[((size_t)b * M + k) * p.K + i] = src >= 0 ? __ldg(sb + (size_t)k * p.F + src) : (hb != nullptr ? __ldg(hb + (size_t)k * p.K + i + p.F) : 0.f);
+    }
+  }
   const float gain = (float)M;
   float* ob = p.out + (size_t)b * M * p.F;
 #pragma unroll
@@ -311,20 +326,6 @@ __global__ void __launch_bounds__(kDirectThreads) synthesis_direct_kernel(Synthe
         if (p0 + c < M) o[c] = acc[r][c] * gain;
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// streaming history roll:  new = last W of (old ++ block), per row.  rows = B (analysis, W = L,
-// block length T) or B*M (synthesis, W = K, block length F).
-// ---------------------------------------------------------------------------------------------
-__global__ void roll_history_kernel(const float* __restrict__ old_h, const float* __restrict__ blk, float* __restrict__ new_h,
-                                    long rows, int W, long Tb) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * W) return;
-  const long row = idx / W;
-  const int i = (int)(idx - row * W);
-  const long src = (long)i + Tb - W;  // position in the block; negative -> still inside old history
-  new_h[idx] = (src >= 0) ? blk[row * Tb + src] : old_h[row * W + i + Tb];
 }
 
 }  // namespace pqmf

@@ -72,12 +72,13 @@ struct H4Shape {
   int bank;            // bytes of one CTA's bank image: [2 ks chunks][96 or 128 rows][16 B]
   int bytes;           // dynamic shared memory
 };
-inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis) {
+inline H4Shape h4_shape(int M, int jlo, int kt, bool pair, bool synthesis, int extra_pad_bytes = 0) {
   H4Shape g;
   g.jlo = jlo;
   g.kt = kt;
   g.ks = (kt + 64 - M + 15) / 16;
-  const int pad_bytes = synthesis ? 3 * 2 * M : 0;               // synthesis shifts its windows by up to 3 frames (alignment)
+  const int pad_bytes = (synthesis ? 3 * 2 * M : 0) + extra_pad_bytes;  // synthesis shifts its windows by up to 3 frames (alignment); streaming
+                                                                        // blocks may shift theirs to make the history whole rows
   g.rows = kH4Rows + (32 * g.ks + pad_bytes - 1) / 128;
   g.plane = ((g.rows * 128 + 1023) / 1024) * 1024;
   g.bank = g.ks * 2 * (pair ? 96 : 128) * 16;

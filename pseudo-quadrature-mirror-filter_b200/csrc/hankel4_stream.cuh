@@ -1,4 +1,4 @@
-// Streaming (cached) blocks of n_band 16 on the Hankel-4 tensor-core kernels (hankel4.cuh).
+// Streaming (cached) blocks of n_band 8 / 16 / 32 on the Hankel-4 tensor-core kernels (hankel4.cuh).
 //
 // A streaming block is short (config 3: 2048 samples = 32 operand rows of 64 samples), so one 128-row MMA tile serves several
 // streams.  Each stream gets its own REGION of plane rows: [history rows | block rows | padding to a multiple of 4 rows].  The
@@ -32,12 +32,12 @@ struct H4AnalysisStreamParams {
   const float* x;         // [B, T]
   const float* hist_in;   // [B, L]: the L samples that preceded x
   float* hist_out;        // [B, L]: the last L samples of x (T >= L)
-  float* y;               // [B, 16, T / 16]
+  float* y;               // [B, M, T / M]
   const uint16_t* bank;
   long T;
   int B, L;
   int parity, trim_lo, trim_hi;
-  int keep;               // y is read back by a later phase of the same kernel: store it without the streaming hint
+  int pad_bytes;          // the region carries more history than the taps need (rounded up to whole rows): windows start this much later
   H4Shape g;
   H4StreamGeom s;
   long n_tiles;
@@ -45,10 +45,10 @@ struct H4AnalysisStreamParams {
 
 // the worker warps' part of streaming analysis (warps 0-7): tiles blockIdx.x, + gridDim.x, ...; `it0` / `bank_phase` continue the
 // barrier sequence when this is a phase of the fused block-step kernel
-template <bool PAIR>
+template <int M, bool PAIR>
 __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStreamParams& p, const H4Smem& sm, uint32_t tmem, uint32_t pfull_leader,
                                                            unsigned n_iter, unsigned it0, unsigned bank_phase, int tid) {
-  constexpr int M = 16, FR = 4, HB = 8;
+  constexpr int FR = 64 / M, HB = M / 2;  // frames per 64-sample row, bands per epilogue thread
   constexpr int NQ = (kH4Rows * 16 + kH4Workers - 1) / kH4Workers;  // 8 float4 per thread cover the 128 region rows of a tile
   const H4Shape& g = p.g;
   const H4StreamGeom& sg = p.s;
@@ -109,7 +109,7 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
       }
     }
   };
-  // D (TMEM) -> y: MMA row i = region t, row q: block row q (frames 4 q .. 4 q + 3) of stream tile * spt + t when q < rows_b
+  // D (TMEM) -> y: MMA row i = region t, row q: block row q (frames FR q .. FR q + FR - 1) of stream tile * spt + t when q < rows_b
   const int i = tid & 127, hb = tid >> 7;
   const int et = i / sg.pitch, eq = i - et * sg.pitch;
   const bool e_row = et < sg.spt && eq < sg.rows_b;
@@ -119,23 +119,31 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
     uint32_t r0[FR][HB], r1[FR][HB];
 #pragma unroll
     for (int dl = 0; dl < FR; ++dl) {
-      ptx::tmem_ld8(taddr + dl * M, r0[dl]);
-      ptx::tmem_ld8(taddr + 64 + dl * M, r1[dl]);
+      h4_tmem_ld<HB>(taddr + dl * M, r0[dl]);
+      h4_tmem_ld<HB>(taddr + 64 + dl * M, r1[dl]);
     }
     ptx::tmem_ld_wait();
     if (!e_row || sidx >= p.B) return;
-    float* yp = p.y + ((size_t)sidx * M + HB * hb) * F + 4 * eq;
+    float* yp = p.y + ((size_t)sidx * M + HB * hb) * F + FR * eq;
 #pragma unroll
     for (int kk = 0; kk < HB; ++kk) {
       float w[FR];
 #pragma unroll
       for (int dl = 0; dl < FR; ++dl) {
-        const uint32_t flip = (((dl + p.parity) & 1) == 0 && (kk & 1)) ? 0x80000000u : 0u;  // global frame parity = parity of dl + frame_parity
+        // global frame parity = parity of (FR eq + dl) + frame_parity; FR eq is even for FR > 1
+        const int fpar = (FR > 1 ? dl : eq) + p.parity;
+        const uint32_t flip = ((fpar & 1) == 0 && (kk & 1)) ? 0x80000000u : 0u;
         w[dl] = __uint_as_float(__float_as_uint(h4_combine(r0[dl][kk], r1[dl][kk])) ^ flip);
       }
-      // a following phase of the same kernel reads these back: plain stores then (L2-coherent), streaming stores otherwise
-      if (p.keep) *reinterpret_cast<float4*>(yp + (size_t)kk * F) = make_float4(w[0], w[1], w[2], w[3]);
-      else __stcs(reinterpret_cast<float4*>(yp + (size_t)kk * F), make_float4(w[0], w[1], w[2], w[3]));
+      float* q = yp + (size_t)kk * F;
+      if constexpr (FR >= 4) {
+#pragma unroll
+        for (int d4 = 0; d4 < FR; d4 += 4) __stcs(reinterpret_cast<float4*>(q + d4), make_float4(w[d4], w[d4 + 1], w[d4 + 2], w[d4 + 3]));
+      } else if constexpr (FR == 2) {
+        __stcs(reinterpret_cast<float2*>(q), make_float2(w[0], w[1]));
+      } else {
+        __stcs(q, w[0]);
+      }
     }
   };
 
@@ -161,7 +169,7 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
   epilogue(prev_tile, (int)(last & 1));
 }
 
-template <bool PAIR>
+template <int M, bool PAIR>
 __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4AnalysisStreamParams p) {
   extern __shared__ __align__(1024) unsigned char h4as_smem[];
   const H4Shape g = p.g;
@@ -174,22 +182,23 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_stream_kernel(H4Ana
   const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;
   const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
   if (warp == kMmaWarp) {
-    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim_lo, p.trim_hi);
+    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, p.pad_bytes, p.trim_lo, p.trim_hi);
   } else {
-    h4_analysis_stream_workers<PAIR>(p, sm, tmem, pfull_leader, n_iter, 0, 0, tid);
+    h4_analysis_stream_workers<M, PAIR>(p, sm, tmem, pfull_leader, n_iter, 0, 0, tid);
   }
   h4_teardown<PAIR>(tmem, warp);
 }
 
 struct H4SynthesisStreamParams {
-  const float* s;          // [B, 16, F]
-  const float* state_in;   // [B, 16, K]: the K = L / 16 frames that preceded s
-  float* state_out;        // [B, 16, K]: the last K frames of s (F >= K)
-  float* out;              // [B, 16 F]
+  const float* s;          // [B, M, F]
+  const float* state_in;   // [B, M, K]: the K = L / M frames that preceded s
+  float* state_out;        // [B, M, K]: the last K frames of s (F >= K)
+  float* out;              // [B, M F]
   const uint16_t* bank;
   long F;
   int B, K;
   int parity, trim_lo, trim_hi;
+  int pad_bytes;           // see H4AnalysisStreamParams
   H4Shape g;
   H4StreamGeom sg;
   long n_tiles;
@@ -197,21 +206,24 @@ struct H4SynthesisStreamParams {
 
 // the worker warps' part of streaming synthesis (warps 0-8).  OWN: the sub-bands were written by an earlier phase of this kernel
 // (by this very CTA: same tile -> stream map), so they are read through L2 instead of the non-coherent path.
-template <bool PAIR, bool OWN>
+template <int M, bool PAIR, bool OWN>
 __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStreamParams& p, const H4Smem& sm, uint32_t tmem, uint32_t pfull_leader,
                                                             unsigned n_iter, unsigned it0, unsigned bank_phase, int tid) {
-  constexpr int M = 16;
+  static_assert(M >= 8, "frame quads of 8-band groups (n_band 4 packs its chunks differently: offline kernels only)");
+  constexpr int FR = 64 / M, NBG = M / 8;  // frames per 128-byte plane row, 8-band groups
   const H4Shape& g = p.g;
   const H4StreamGeom& sg = p.sg;
   const int warp = tid >> 5;
   for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4SynWorkers)
 #pragma unroll
     for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
-  // item (frame quad wq of the tile, band group bg): one plane row = one frame quad at n_band 16
-  const int n_fq = sg.spt * sg.pitch;
+  // item (frame quad wq of the tile, band group bg): four frames x eight bands = four 16-byte chunks per plane.  A region holds
+  // pitch * FR frames; its first hrows * FR frames are history (both multiples of 4: a quad never straddles the boundary)
+  const int n_fq = sg.spt * sg.pitch * FR / 4;
   const int bg = tid / n_fq, wq = tid - bg * n_fq;
-  const bool has_item = tid < 2 * n_fq;
-  const int lt = wq / sg.pitch, lq = wq - lt * sg.pitch;  // region, row within the region
+  const bool has_item = tid < NBG * n_fq;
+  const int region_frames = sg.pitch * FR, hist_fr = sg.hrows * FR, block_fr = sg.rows_b * FR;
+  const int lt = (4 * wq) / region_frames, lf = 4 * wq - lt * region_frames;  // region, first frame of the quad within the region
   float4 v[8];
   auto load_tile = [&](long tile) {
     const long sidx = tile * sg.spt + lt;
@@ -221,10 +233,10 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       const size_t band = (size_t)sidx * M + 8 * bg + kk;
       if (live) {
-        if (lq < sg.hrows) {
-          t = ptx::ldg128_na(reinterpret_cast<const float4*>(p.state_in + band * p.K + (p.K - 4 * sg.hrows) + 4 * lq));
-        } else if (lq - sg.hrows < sg.rows_b) {
-          const float4* src = reinterpret_cast<const float4*>(p.s + band * p.F + 4 * (lq - sg.hrows));
+        if (lf < hist_fr) {
+          t = ptx::ldg128_na(reinterpret_cast<const float4*>(p.state_in + band * p.K + (p.K - hist_fr) + lf));
+        } else if (lf - hist_fr < block_fr) {
+          const float4* src = reinterpret_cast<const float4*>(p.s + band * p.F + (lf - hist_fr));
           t = OWN ? ptx::ldg128_cg(src) : ptx::ldg128_na(src);
         }
       }
@@ -233,12 +245,12 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
   };
   // sigma(k, n): odd bands flip on even global frames; regions and history lengths are multiples of 4 frames, so the parity is j's
   const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
-  const int fb = 4 * (lq - sg.hrows);  // first frame of this thread's quad within the block (negative: history)
+  const int fb = lf - hist_fr;  // first frame of this thread's quad within the block (negative: history)
   auto convert = [&](int pb, long tile) {
     if (!has_item) return;
     unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
     const long sidx = tile * sg.spt + lt;
-    if (fb >= p.F - p.K && lq - sg.hrows < sg.rows_b && sidx < p.B) {  // the last K frames of the block become the next history
+    if (fb >= p.F - p.K && fb < block_fr && sidx < p.B) {  // the last K frames of the block become the next history
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk)
         *reinterpret_cast<float4*>(p.state_out + ((size_t)sidx * M + 8 * bg + kk) * p.K + (fb - (p.F - p.K))) = v[kk];
@@ -257,7 +269,7 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
       split2_f16s(w[2], w[3], h1.y, h2.y);
       split2_f16s(w[4], w[5], h1.z, h2.z);
       split2_f16s(w[6], w[7], h1.w, h2.w);
-      const uint32_t o = sw128_offset((uint32_t)(4 * wq + j) * 32u + 16u * bg);
+      const uint32_t o = sw128_offset((uint32_t)(4 * wq + j) * (2u * M) + 16u * bg);
       *reinterpret_cast<uint4*>(p1 + o) = h1;
       *reinterpret_cast<uint4*>(p1 + g.plane + o) = h2;
     }
@@ -326,7 +338,7 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
   if (warp < 8) epilogue(prev_tile, (int)(last & 1));
 }
 
-template <bool PAIR>
+template <int M, bool PAIR>
 __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H4SynthesisStreamParams p) {
   extern __shared__ __align__(1024) unsigned char h4ss_smem[];
   const H4Shape g = p.g;
@@ -339,9 +351,9 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_stream_kernel(H
   const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;
   const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
   if (warp == kMmaWarp) {
-    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, 0, p.trim_lo, p.trim_hi);  // (o - ehi) is a multiple of 4 here: no alignment pad
+    if (rank == 0) h4_issuer_loop<PAIR>(sm, g, tmem, n_iter, p.pad_bytes, p.trim_lo, p.trim_hi);
   } else {
-    h4_synthesis_stream_workers<PAIR, false>(p, sm, tmem, pfull_leader, n_iter, 0, 0, tid);
+    h4_synthesis_stream_workers<M, PAIR, false>(p, sm, tmem, pfull_leader, n_iter, 0, 0, tid);
   }
   h4_teardown<PAIR>(tmem, warp);
 }
@@ -371,15 +383,17 @@ inline int h4_stream_launch(Kern kern, Params p, int threads, H4Configured& conf
   cfg.numAttrs = 2;
   return (int)cudaLaunchKernelEx(&cfg, kern, p);
 }
+template <int M>
 inline int h4_launch_analysis_stream(H4AnalysisStreamParams p, cudaStream_t st) {
   static H4Configured configured;
   p.n_tiles = (p.B + p.s.spt - 1) / p.s.spt;
-  return h4_stream_launch(h4_analysis_stream_kernel<true>, p, kH4Threads, configured, st);
+  return h4_stream_launch(h4_analysis_stream_kernel<M, true>, p, kH4Threads, configured, st);
 }
+template <int M>
 inline int h4_launch_synthesis_stream(H4SynthesisStreamParams p, cudaStream_t st) {
   static H4Configured configured;
   p.n_tiles = (p.B + p.sg.spt - 1) / p.sg.spt;
-  return h4_stream_launch(h4_synthesis_stream_kernel<true>, p, kH4SynThreads, configured, st);
+  return h4_stream_launch(h4_synthesis_stream_kernel<M, true>, p, kH4SynThreads, configured, st);
 }
 
 }  // namespace pqmf

@@ -60,10 +60,10 @@ int launch_analysis_direct(pqmf::AnalysisDirectParams p, int B, cudaStream_t st)
 }
 
 int analysis_direct(const float* x, const float* hist, float* y, const float* hk, int B, long T, long n_frames, int M, int L,
-                    int off, int parity, int nosign, cudaStream_t st, pqmf::PcmIn pcm = pqmf::PcmIn{nullptr, 1, 0}) {
+                    int off, int parity, int nosign, cudaStream_t st, pqmf::PcmIn pcm = pqmf::PcmIn{nullptr, 1, 0}, float* hist_out = nullptr) {
   if (n_frames == 0 || B == 0) return PQMF_OK;
   pqmf::AnalysisDirectParams p{};
-  p.x = x; p.hist = hist; p.y = y; p.hk = hk; p.in = pcm;
+  p.x = x; p.hist = hist; p.y = y; p.hk = hk; p.in = pcm; p.hist_out = hist_out;
   p.T = T; p.n_frames = n_frames; p.M = M; p.L = L; p.off = off; p.parity = parity & 1; p.nosign = nosign;
   p.m_shift = log2_exact(M);
   int jc = (512 / M) * M;
@@ -95,10 +95,11 @@ int launch_synthesis_direct(pqmf::SynthesisDirectParams p, int B, cudaStream_t s
 }
 
 int synthesis_direct(const float* s, const float* hist, float* out, const float* hk, int B, long F, int M, int L, int off2,
-                     int parity, int nosign, cudaStream_t st, int16_t* pcm_out = nullptr, int C = 1, const pqmf::BandTable* bands = nullptr) {
+                     int parity, int nosign, cudaStream_t st, int16_t* pcm_out = nullptr, int C = 1, const pqmf::BandTable* bands = nullptr,
+                     float* hist_out = nullptr) {
   if (F == 0 || B == 0) return PQMF_OK;
   pqmf::SynthesisDirectParams p{};
-  p.s = s; p.hist = hist; p.out = out; p.hk = hk; p.pcm_out = pcm_out; p.C = C;
+  p.s = s; p.hist = hist; p.out = out; p.hk = hk; p.pcm_out = pcm_out; p.C = C; p.hist_out = hist_out;
   if (bands) p.bands = *bands;
   p.F = F; p.M = M; p.L = L; p.K = L / M; p.off2 = off2; p.parity = parity & 1; p.nosign = nosign;
   p.dlo = (int)pqmf::floor_div(-(long)off2, M);
@@ -110,15 +111,6 @@ int synthesis_direct(const float* s, const float* hist, float* out, const float*
   if (M <= 4) return launch_synthesis_direct<1, 4, true>(p, B, st);
   if (M <= 8) return launch_synthesis_direct<2, 4, true>(p, B, st);
   return launch_synthesis_direct<4, 4, true>(p, B, st);
-}
-
-int roll_history(const float* old_h, const float* blk, float* new_h, long rows, int W, long Tb, cudaStream_t st) {
-  const long n = rows * W;
-  if (n == 0) return PQMF_OK;
-  const int threads = 256;
-  pqmf::roll_history_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(old_h, blk, new_h, rows, W, Tb);
-  ++g_launches;
-  return cuda_status();
 }
 
 bool bad_dims(int B, long n, int M, int L) { return B < 0 || n < 0 || M < 2 || L < M || L > (1 << 16); }
@@ -298,44 +290,66 @@ int h4_synthesis(const float* s, float* out, const float* tables, int B, long F,
 
 // ---- streaming blocks of n_band 16 on the Hankel kernels (hankel4_stream.cuh): several streams per MMA tile.  Any refusal
 //      (short blocks, few streams, odd sizes, a context without CTA pairs) returns UNSUPPORTED and the fold kernels run instead ----
-int h4_analysis_stream(const float* x, float* y, const float* tables, const float* state_in, float* state_out, int B, long T, int L,
+int h4_analysis_stream(const float* x, float* y, const float* tables, const float* state_in, float* state_out, int B, long T, int M, int L,
                        int parity, unsigned flags, cudaStream_t st) {
   int jlo, kt;
   h4_taps(flags, jlo, kt);
   if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
-  if ((L - jlo) % 64 != 0 || T % 256 != 0 || T < L) return PQMF_ERR_UNSUPPORTED;
-  const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(T, L - jlo);
+  // the region of a stream starts with its history as WHOLE plane rows: where the taps need a fraction of a row (n_band 8: 224 samples)
+  // the region carries the next multiple of 64 (the state holds L samples) and every window starts that much later (pad_bytes)
+  const int hist = ((L - jlo + 63) / 64) * 64;
+  if (hist > L || T % 256 != 0 || T < L) return PQMF_ERR_UNSUPPORTED;
+  const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(T, hist);
   if (sg.pitch > pqmf::kH4Rows || sg.spt < 1 || (B + sg.spt - 1) / sg.spt < 96) return PQMF_ERR_UNSUPPORTED;
   if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)state_in | (uintptr_t)state_out) % 16) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4AnalysisStreamParams p{};
   p.x = x; p.hist_in = state_in; p.hist_out = state_out; p.y = y; p.T = T; p.B = B; p.L = L; p.parity = parity & 1;
   p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);
-  p.g = pqmf::h4_shape(16, jlo, kt, true, false);
+  p.pad_bytes = 2 * (hist - (L - jlo));
+  p.g = pqmf::h4_shape(M, jlo, kt, true, false, p.pad_bytes);
   p.s = sg;
-  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset);
-  if (pqmf::h4_launch_analysis_stream(p, st) != 0) {
+  p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L));
+  int e = -2;
+  switch (M) {
+    case 8: e = pqmf::h4_launch_analysis_stream<8>(p, st); break;
+    case 16: e = pqmf::h4_launch_analysis_stream<16>(p, st); break;
+    case 32: e = pqmf::h4_launch_analysis_stream<32>(p, st); break;
+    default: break;
+  }
+  if (e != 0) {
     (void)cudaGetLastError();
     return PQMF_ERR_UNSUPPORTED;
   }
   return 0;
 }
-int h4_synthesis_stream(const float* s, float* out, const float* tables, const float* state_in, float* state_out, int B, long F, int L,
+int h4_synthesis_stream(const float* s, float* out, const float* tables, const float* state_in, float* state_out, int B, long F, int M, int L,
                         int parity, unsigned flags, cudaStream_t st) {
   int jlo, kt;
   h4_taps(flags, jlo, kt);
   if (kt == 0 || (flags & (PQMF_FLAG_H4_SPLIT | PQMF_FLAG_NO_PAIR | PQMF_FLAG_FOLD))) return PQMF_ERR_UNSUPPORTED;
-  const int K = L / 16, hist_frames = (jlo + kt) / 16;  // = ehi + 1: with o = -1 the window of output frame f starts at sub-band frame f - hist_frames
-  if (hist_frames % 4 != 0 || hist_frames > K || F % 16 != 0 || F < K) return PQMF_ERR_UNSUPPORTED;
-  const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(F * 16, hist_frames * 16);
+  const int K = L / M, taps_frames = (jlo + kt) / M;  // = ehi + 1: with o = -1 the window of output frame f starts at sub-band frame f - taps_frames
+  // history and block are whole plane rows (64 / M frames each) and whole frame quads: the region carries the history rounded up to
+  // rows (the state holds K frames) and the windows start that many frames later (pad_bytes)
+  const int hist_frames = ((taps_frames * M + 63) / 64) * 64 / M;
+  if (hist_frames % 4 != 0 || hist_frames > K || (F * M) % 256 != 0 || F % 4 != 0 || F < K) return PQMF_ERR_UNSUPPORTED;
+  const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(F * M, hist_frames * M);
   if (sg.pitch > pqmf::kH4Rows || sg.spt < 1 || (B + sg.spt - 1) / sg.spt < 96) return PQMF_ERR_UNSUPPORTED;
   if (((uintptr_t)s | (uintptr_t)state_in | (uintptr_t)state_out) % 16 || ((uintptr_t)out % 32)) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisStreamParams p{};
   p.s = s; p.state_in = state_in; p.state_out = state_out; p.out = out; p.F = F; p.B = B; p.K = K; p.parity = parity & 1;
   p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
-  p.g = pqmf::h4_shape(16, jlo, kt, true, true);
+  p.pad_bytes = 2 * M * (hist_frames - taps_frames);
+  p.g = pqmf::h4_shape(M, jlo, kt, true, true, p.pad_bytes);
   p.sg = sg;
-  p.bank = reinterpret_cast<const uint16_t*>(tables + kH4PairOffset + kH4PairImageFloats);
-  if (pqmf::h4_launch_synthesis_stream(p, st) != 0) {
+  p.bank = reinterpret_cast<const uint16_t*>(tables + h4_pair_offset(M, L) + h4_pair_floats(M, L));
+  int e = -2;
+  switch (M) {
+    case 8: e = pqmf::h4_launch_synthesis_stream<8>(p, st); break;
+    case 16: e = pqmf::h4_launch_synthesis_stream<16>(p, st); break;
+    case 32: e = pqmf::h4_launch_synthesis_stream<32>(p, st); break;
+    default: break;
+  }
+  if (e != 0) {
     (void)cudaGetLastError();
     return PQMF_ERR_UNSUPPORTED;
   }
@@ -757,13 +771,18 @@ int pqmf_analysis_stream_f32(const float* x, float* y, const float* hk, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const long F = T / M;
   if (use_fast(M, L, tables, flags) && pqmf::hankel16_analysis_ok(x, y, T, F)) {
-    if (h4_analysis_stream(x, y, tables, state_in, state_out, B, T, L, frame_parity, flags, st) == 0) { ++g_launches; return 0; }
+    if (h4_analysis_stream(x, y, tables, state_in, state_out, B, T, 16, L, frame_parity, flags, st) == 0) { ++g_launches; return 0; }
     int e = fast_analysis(x, state_in, y, state_out, tables, B, T, F, L, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
-  int e = analysis_direct(x, state_in, y, hk, B, T, F, M, L, L, frame_parity, 0, st);
-  if (e) return e;
-  return roll_history(state_in, x, state_out, B, L, T, st);
+  // n_band 8 / 32 with many streams: the streaming Hankel kernels (same tiles-of-streams scheme as n_band 16)
+  if (!pqmf::hankel16_supported(M, L) && use_h4_family(M, L, tables, flags) && (M == 8 || M == 32) &&
+      h4_analysis_stream(x, y, tables, state_in, state_out, B, T, M, L, frame_parity, flags, st) == 0) {
+    ++g_launches;
+    return 0;
+  }
+  // fp32 direct form; the CTA of each row's last frame tile also rolls that row's history (no separate launch)
+  return analysis_direct(x, state_in, y, hk, B, T, F, M, L, L, frame_parity, 0, st, pqmf::PcmIn{nullptr, 1, 0}, state_out);
 }
 
 int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const float* tables, const float* state_in,
@@ -777,13 +796,16 @@ int pqmf_synthesis_stream_f32(const float* s, float* out, const float* hk, const
   const int K = L / M;
   // history frames sit K frames before frame 0 of the block: their parity offset is (frame_parity - K)
   if (use_fast(M, L, tables, flags) && pqmf::hankel16_synthesis_ok(s, out, n_frames)) {
-    if (h4_synthesis_stream(s, out, tables, state_in, state_out, B, n_frames, L, frame_parity, flags, st) == 0) { ++g_launches; return 0; }
+    if (h4_synthesis_stream(s, out, tables, state_in, state_out, B, n_frames, 16, L, frame_parity, flags, st) == 0) { ++g_launches; return 0; }
     int e = fast_synthesis(s, state_in, out, state_out, tables, B, n_frames, -M, frame_parity & 1, flags, st);
     if (e != PQMF_ERR_UNSUPPORTED) { g_launches += (e == 0); return e; }
   }
-  int e = synthesis_direct(s, state_in, out, hk, B, n_frames, M, L, -M, frame_parity, 0, st);
-  if (e) return e;
-  return roll_history(state_in, s, state_out, (long)B * M, K, n_frames, st);
+  if (!pqmf::hankel16_supported(M, L) && use_h4_family(M, L, tables, flags) && (M == 8 || M == 32) &&
+      h4_synthesis_stream(s, out, tables, state_in, state_out, B, n_frames, M, L, frame_parity, flags, st) == 0) {
+    ++g_launches;
+    return 0;
+  }
+  return synthesis_direct(s, state_in, out, hk, B, n_frames, M, L, -M, frame_parity, 0, st, nullptr, 1, nullptr, state_out);
 }
 
 int pqmf_stream_step_f32(const float* x, float* y, float* out, const float* hk, const float* tables, const float* xstate_in, float* xstate_out,

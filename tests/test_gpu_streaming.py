@@ -195,3 +195,31 @@ def test_fused_block_step_equals_the_two_calls(pq, streams, block):
     y1 = one.forward_stream(x[..., block : 2 * block].contiguous())
     o1 = one.inverse_stream(y1)
     assert torch.equal(torch.cat([y0, y1], -1), y_e[..., : 2 * block // 16]) and torch.equal(torch.cat([o0, o1], -1), out_e[..., : 2 * block])
+
+
+@pytest.mark.parametrize("m,streams,block", ((8, 300, 2048), (32, 300, 2048), (8, 1000, 512), (32, 290, 4096), (8, 7, 2048), (32, 5, 1024)))
+def test_streaming_other_band_counts(golden, pq, m, streams, block):
+    """n_band 8 and 32: many streams run the streaming Hankel kernels (tiles of several streams, as n_band 16), few streams the fp32
+    direct form with the history roll fused into the kernel.  Against the float64 streaming oracle, the offline kernels and the
+    plain-fp32 module."""
+    hk = golden(f"bank_M{m}.npz")["hk"]
+    length = hk.shape[1]
+    n_blocks = 3
+    x = O.audio_like((streams, 1, n_blocks * block), 11 * m + block)
+    xd = torch.from_numpy(x).cuda()
+    mod = pq.CachedPQMF(100, m).cuda()
+    y_s, out_s = _run_stream(mod, xd, block)
+    st = O.StreamState(streams, m, length)
+    y64 = O.stream_analysis(x[:, 0], hk, st)
+    o64 = O.stream_synthesis(y_s.cpu().numpy(), hk, st)
+    assert np.abs(y_s.cpu().numpy() - y64).max() <= TOL / 2
+    assert np.abs(out_s.cpu().numpy()[:, 0] - o64).max() <= TOL / 2
+    xz = torch.cat([torch.zeros(streams, 1, length // 2, device="cuda"), xd], dim=-1)
+    assert (y_s - mod.forward(xz)[..., : y_s.shape[-1]]).abs().max().item() <= 3e-6
+    plain = pq.CachedPQMF(100, m, fp32=True).cuda()
+    y_p, out_p = _run_stream(plain, xd, block)
+    assert (y_p - y_s).abs().max().item() <= 3e-6 and (out_p - out_s).abs().max().item() <= 8e-6
+    lat = mod.cumulative_delay
+    if out_s.shape[-1] > 4 * lat:
+        err = out_s[..., lat:] - xd[..., :-lat]
+        assert (10 * torch.log10((xd[..., :-lat] ** 2).sum() / (err ** 2).sum())).item() > 30.0
