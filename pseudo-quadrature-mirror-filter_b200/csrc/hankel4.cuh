@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
         const int o = tid + kH4Workers * r;
         const long s = s0 + 8L * o;
         if (bb < n_rows && o < n_octs && s >= 0 && s < p.T) {
-          if constexpr (PCM) pcm_load8(p.in, bb, s, p.T, x0[r]);
+          if constexpr (PCM) pcm_load8_raw(p.in, bb, s, p.T, x0[r]);   // raw int16 words: converted when the tile is consumed
           else ptx::ldg256_na(xrow + s, x0[r]);
         } else {
 #pragma unroll
@@ -317,13 +317,17 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     };
     // fp32 window -> two fp16 planes (SWIZZLE_128B rows of 64 samples, one 16-byte chunk per load).  planes[pb] were last read by
     // the MMAs of tile it-2, whose completion this thread observed before draining tile it-2.
-    auto convert = [&](int pb) {
+    auto convert = [&](int pb, unsigned bb, unsigned cc) {
       unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
       unsigned char* p2 = p1 + g.plane;
 #pragma unroll
       for (int r = 0; r < NO; ++r) {
         const int o = tid + kH4Workers * r;
         if (o < n_octs) {
+          if constexpr (PCM) {  // the registers hold raw PCM words where the load was live (zeros stay zeros: 0 is not a valid raw mono / stereo pattern to convert)
+            const long s = (long)cc * kH4TileSamples + g.jlo - p.off + 8L * o;
+            if (bb < n_rows && s >= 0 && s < p.T) pcm_convert8(p.in, bb, x0[r]);
+          }
           uint4 a, bq;
           split2_f16s(x0[r][0], x0[r][1], a.x, bq.x);
           split2_f16s(x0[r][2], x0[r][3], a.y, bq.y);
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       H4_STAMP(0);
-      convert(pb);
+      convert(pb, b, c);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
       if (it + 1 < n_iter) load_window(b1, c1);  // consumed at the top of the next iteration

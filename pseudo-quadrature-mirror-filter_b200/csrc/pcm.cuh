@@ -33,32 +33,46 @@ __device__ __forceinline__ int16_t pcm_quantise(float v) {
   return (int16_t)(q < -32768.f ? -32768.f : (q > 32767.f ? 32767.f : q));
 }
 
-// eight consecutive samples s .. s + 7 of row b (s a multiple of 8, T a multiple of 8): one 16-byte load for mono, one 32-byte load
-// for stereo (either channel or the down-mix), element-wise otherwise
-__device__ __forceinline__ void pcm_load8(const PcmIn& in, long b, long s, long T, float (&v)[8]) {
-  constexpr float kInv = 1.0f / 32768.0f;
+// both int16 halves of a 32-bit word as float / 32768, exactly, without I2F: XOR the sign bits (offset binary u = v + 32768), drop each
+// half into the mantissa of 2^23 (PRMT), and one FMA maps 2^23 + u to (u - 32768) / 32768
+__device__ __forceinline__ void pcm_pair(int word, float& lo, float& hi) {
+  const uint32_t w = (uint32_t)word ^ 0x80008000u;
+  lo = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), 1.0f / 32768.0f, -257.0f);
+  hi = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), 1.0f / 32768.0f, -257.0f);
+}
+
+// eight consecutive samples s .. s + 7 of row b (s a multiple of 8, T a multiple of 8), in two steps so that a kernel can keep the RAW
+// words in registers across its prefetch distance and convert when it consumes them: pcm_load8_raw issues one 16-byte load for mono,
+// one 32-byte load for stereo (either channel or the down-mix) and converts on the spot only beyond two channels (element-wise loads);
+// pcm_convert8 turns the raw words into floats / 32768.
+__device__ __forceinline__ void pcm_load8_raw(const PcmIn& in, long b, long s, long T, float (&v)[8]) {
   if (in.C == 1) {
     const int4 raw = __ldg(reinterpret_cast<const int4*>(in.pcm + (size_t)b * T + s));
-    const int w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = (float)(int16_t)(w[i] & 0xFFFF) * kInv;
-      v[2 * i + 1] = (float)(int16_t)(w[i] >> 16) * kInv;
-    }
+    v[0] = __int_as_float(raw.x); v[1] = __int_as_float(raw.y); v[2] = __int_as_float(raw.z); v[3] = __int_as_float(raw.w);
   } else if (in.C == 2) {
     const long clip = in.downmix ? b : (b >> 1);
-    const int ch = in.downmix ? 0 : (int)(b & 1);
     const int4* src = reinterpret_cast<const int4*>(in.pcm + ((size_t)clip * T + s) * 2);
     const int4 r0 = __ldg(src), r1 = __ldg(src + 1);
-    const int w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};  // one WAV frame (left, right) per word
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float l = (float)(int16_t)(w[i] & 0xFFFF) * kInv, r = (float)(int16_t)(w[i] >> 16) * kInv;
-      v[i] = in.downmix ? (l + r) / 2.0f : (ch ? r : l);
-    }
+    v[0] = __int_as_float(r0.x); v[1] = __int_as_float(r0.y); v[2] = __int_as_float(r0.z); v[3] = __int_as_float(r0.w);
+    v[4] = __int_as_float(r1.x); v[5] = __int_as_float(r1.y); v[6] = __int_as_float(r1.z); v[7] = __int_as_float(r1.w);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = pcm_sample(in, b, s + i, T);
+  }
+}
+__device__ __forceinline__ void pcm_convert8(const PcmIn& in, long b, float (&v)[8]) {
+  if (in.C == 1) {
+    const int w[4] = {__float_as_int(v[0]), __float_as_int(v[1]), __float_as_int(v[2]), __float_as_int(v[3])};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pcm_pair(w[i], v[2 * i], v[2 * i + 1]);
+  } else if (in.C == 2) {
+    const int ch = in.downmix ? 0 : (int)(b & 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // one WAV frame (left, right) per word
+      float l, r;
+      pcm_pair(__float_as_int(v[i]), l, r);
+      v[i] = in.downmix ? (l + r) / 2.0f : (ch ? r : l);
+    }
   }
 }
 
