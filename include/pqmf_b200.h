@@ -68,8 +68,8 @@ const char* pqmf_strerror(int code);
 
 /* Which kernel family a call with these parameters would use: 0 = register-tiled direct form (generic),
  * 1 = the tensor-core kernels: n_band 16 / L 512 (Hankel-4 offline, fold + modulation for streaming blocks and small
- * batches and few streams, Hankel-4 streaming for many streams) and n_band 8 / 32 / 64 (Hankel offline, large batches).
- * `tables` may be NULL. */
+ * batches and few streams, Hankel-4 streaming for many streams) and n_band 4 / 8 / 32 / 64 (Hankel offline, large batches; n_band 8 / 32
+ * also streaming with many streams).  PQMF_FLAG_FP32 and PQMF_FLAG_NO_SIGN always give 0.  `tables` may be NULL. */
 int pqmf_path_for(int M, int L, const float* tables, unsigned flags);
 
 /* ---- coefficient tables for the fast path (host side, one-off; replaces nothing in the reference:
