@@ -46,4 +46,38 @@ for case in range(12):
         ea, es = float((y - yr).abs().max()), float((o - orf).abs().max())
         if not (ea <= 3e-6 and es <= 6e-6):
             print("STREAM MISMATCH", dict(att=att, block=block, streams=streams, i=i, ea=ea, es=es)); sys.exit(1)
+# round 2: streaming at n_band 8 / 32, PCM in / out (mono, stereo, down-mix), reconstruct(), process_stream()
+for case in range(16):
+    m = random.choice((8, 16, 32))
+    att = random.choice((100, 100, 80))
+    block = random.choice((512, 1024, 2048, 4096)) * (2 if m == 32 else 1)
+    streams = random.choice((300, 400, 1000)) * (2 if block <= 1024 else 1)
+    mod = pq.CachedPQMF(att, m).cuda(); ref = pq.CachedPQMF(att, m, fp32=True).cuda()
+    x = (0.5 * torch.randn(streams, 1, 3 * block, device="cuda")).clamp_(-1, 1)
+    for i in range(3):
+        xb = x[..., i * block:(i + 1) * block].contiguous()
+        o, y = mod.process_stream(xb)
+        yr = ref.forward_stream(xb)
+        orf = ref.inverse_stream(y)
+        ea, es = float((y - yr).abs().max()), float((o - orf).abs().max())
+        if not (ea <= 3e-6 and es <= 8e-6):
+            print("STREAM-M MISMATCH", dict(m=m, att=att, block=block, streams=streams, i=i, ea=ea, es=es)); sys.exit(1)
+for case in range(16):
+    m = random.choice((4, 8, 16, 16, 32))
+    c = random.choice((1, 1, 2, 2, 3))
+    t = random.choice((8192, 16384, 32768, 40960)) // m * m
+    clips = max(1, -(-random.choice((96, 100, 130)) // (c * -(-t // 8192))))
+    mod = pq.CachedPQMF(100, m).cuda(); ref = pq.CachedPQMF(100, m, fp32=True).cuda()
+    pcm = torch.randint(-32768, 32768, (clips, t, c), device="cuda", dtype=torch.int32).to(torch.int16)
+    xf = (pcm.to(torch.float32) / 32768.0).transpose(1, 2).contiguous()
+    y, yr = mod.forward_pcm16(pcm), ref(xf)
+    if float((y - yr).abs().max()) > 3e-6:
+        print("PCM ANALYSIS MISMATCH", dict(m=m, c=c, t=t, clips=clips)); sys.exit(1)
+    q, qr = mod.inverse_pcm16(yr), torch.clamp(torch.round(ref.inverse(yr) * 32768.0), -32768, 32767).to(torch.int16).transpose(1, 2)
+    if int((q.to(torch.int32) - qr.to(torch.int32)).abs().max()) > 1:
+        print("PCM SYNTHESIS MISMATCH", dict(m=m, c=c, t=t, clips=clips)); sys.exit(1)
+    if c > 1 and float((mod.forward_pcm16(pcm, True) - ref(xf.mean(1, keepdim=True))).abs().max()) > 3e-6:
+        print("PCM DOWNMIX MISMATCH", dict(m=m, c=c, t=t, clips=clips)); sys.exit(1)
+    if not torch.equal(mod.reconstruct(xf), mod.process(xf)[0]):
+        print("RECONSTRUCT MISMATCH", dict(m=m, c=c, t=t, clips=clips)); sys.exit(1)
 print("fuzz ok; worst |hankel - direct| per (n_band, attenuation):", {k: (f"{v[0]:.1e}", f"{v[1]:.1e}") for k, v in sorted(worst.items())})
