@@ -1,13 +1,14 @@
 """Golden outputs of the reference's three WRAPPERS, produced by running them -- unmodified, on top of the reference's own pqmf.py --
 in the dev container:
 
-    python oracle/fetch_ref_wrappers.py && python tests/golden/make_golden_wrappers.py      # needs /root/reference
+    python tests/golden/make_golden_wrappers.py      # needs /root/reference
 
 tests/test_gpu_reference_wrappers.py runs the same wrapper files on CUDA on top of the DROP-IN (dropin/pqmf.py, dropin/PQMF/) and
 compares with these.  Written: tests/golden/wrappers.npz."""
 import importlib.util
 import os
 import sys
+import tempfile
 import types
 
 import numpy as np
@@ -18,7 +19,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 import make_golden as G  # noqa: E402  (cached_conv stand-in, REF)
 
-WRAPPERS = os.path.join(ROOT, "oracle", "_ref", "wrappers")
+sys.path.insert(0, ROOT)
+from oracle import fetch_ref_wrappers  # noqa: E402
+
+WRAPPERS = tempfile.mkdtemp(prefix="ref_wrappers_")
 
 
 def load_module(name, path):
@@ -30,6 +34,7 @@ def load_module(name, path):
 
 
 def main():
+    assert fetch_ref_wrappers.fetch() and fetch_ref_wrappers.unpack(WRAPPERS), "needs /root/reference"
     G.install_cached_conv_stand_in()
     sys.path.insert(0, G.REF)                      # `from pqmf import CachedPQMF`  -> the reference's pqmf.py
     pkg = types.ModuleType("PQMF")                 # `from PQMF.pqmf import ...`     -> the same file, as the wrappers' package name

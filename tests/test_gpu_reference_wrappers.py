@@ -1,7 +1,8 @@
 """The reference's own wrapper scripts, UNCHANGED, running on CUDA on top of the drop-in (north_star: "usable unchanged by
-PQMFWrapper.py and both pitch-shifter wrappers").  The wrapper files are the verbatim copies that oracle/fetch_ref_wrappers.py puts
-into oracle/_ref/wrappers/ (git-ignored, travels to the GPU box); the expected outputs in tests/golden/wrappers.npz were produced by
-the same files on top of the REFERENCE's pqmf.py (tests/golden/make_golden_wrappers.py)."""
+PQMFWrapper.py and both pitch-shifter wrappers").  The wrapper files come, verbatim, out of the archive that
+oracle/fetch_ref_wrappers.py packs where /root/reference is mounted (oracle/_ref/wrappers.tar: git-ignored, travels to the GPU box) and
+are unpacked into a temporary directory here; the expected outputs in tests/golden/wrappers.npz were produced by the same files on top
+of the REFERENCE's pqmf.py (tests/golden/make_golden_wrappers.py)."""
 import importlib.util
 import os
 import sys
@@ -11,11 +12,12 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WRAPPERS = os.path.join(ROOT, "oracle", "_ref", "wrappers")
+ARCHIVE = os.path.join(ROOT, "oracle", "_ref", "wrappers.tar")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.path.isfile(os.path.join(WRAPPERS, "PQMFWrapper.py")),
-                                 reason="oracle/_ref/wrappers missing: run oracle/fetch_ref_wrappers.py where /root/reference is mounted")]
+              pytest.mark.skipif(not os.path.isfile(ARCHIVE),
+                                 reason="oracle/_ref/wrappers.tar missing: run oracle/fetch_ref_wrappers.py where /root/reference is mounted")]
 TOL = 1e-5
+WRAPPERS = ""  # set by the fixture: where the archive was unpacked
 
 
 def _load(name, path):
@@ -27,9 +29,16 @@ def _load(name, path):
 
 
 @pytest.fixture(scope="module")
-def dropin_on_path():
+def dropin_on_path(tmp_path_factory):
     """`from pqmf import CachedPQMF` and `from PQMF.pqmf import CachedPQMF` resolve to the drop-in; the vocoder the Pvoc wrapper imports
     as PQMF.PitchShifterPvoc.VocoderPitchShifter resolves to the reference's own file."""
+    global WRAPPERS
+    sys.path.insert(0, ROOT)
+    from oracle import fetch_ref_wrappers
+
+    WRAPPERS = str(tmp_path_factory.mktemp("ref_wrappers"))
+    assert fetch_ref_wrappers.unpack(WRAPPERS)
+    del sys.path[0]
     sys.path[:0] = [os.path.join(ROOT, "dropin"), ROOT]
     for name in ("pqmf", "PQMF", "PQMF.pqmf"):
         sys.modules.pop(name, None)
