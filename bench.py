@@ -516,6 +516,11 @@ def other_configs(torch, dist, pq, dev, mod, x, peak, n_gpus, distributed):
                                      "frac": round(16 * n / ((ta + ts) * 1e-3) * 1e-9 / peak, 4)}
             del y
             out["single_stream_latency"] = bench_single_stream_latency(torch, pq, dev)
+            # configs[0]: one clip of flute.wav's padded length (303 104 samples, batch 1), forward + inverse: launch-bound on a GPU
+            x1 = (0.5 * torch.randn(1, 1, 303104, device=dev)).clamp_(-1, 1)
+            t1, _ = _sustained(torch, lambda: mod.inverse(mod(x1)), 0.2, min_steps=50)
+            out["config1"] = {"workload": "configs[0]: one 303 104-sample clip (flute.wav padded), n_band 16, forward + inverse, synthetic samples",
+                              "ms_per_step": round(t1, 4), "value": round(303104 / t1 * 1e-3, 1), "unit": UNIT}
         out["config3"] = entry(bench_config3(torch, pq, dev, 0.5))
         r4 = bench_config4(torch, pq, dev, 2.0)
         per = {}

@@ -385,6 +385,17 @@ at::Tensor synthesis_stream_autograd(const at::Tensor& s, const at::Tensor& hk, 
   return op.call(s, hk, tables, state_in, state_out, frame_parity, flags);
 }
 
+std::tuple<at::Tensor, at::Tensor> stream_step_autograd(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, const at::Tensor& xs_in,
+                                                        at::Tensor xs_out, const at::Tensor& ss_in, at::Tensor ss_out, int64_t parity_in,
+                                                        int64_t parity_out, int64_t flags) {
+  TORCH_CHECK(!(at::GradMode::is_enabled() && x.requires_grad()),
+              "pqmf_b200::stream_step is not differentiable (streaming mode carries state across calls); use forward() / inverse() for "
+              "training or wrap the call in torch.no_grad()");
+  at::AutoDispatchBelowADInplaceOrView guard;
+  static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("pqmf_b200::stream_step", "").typed<decltype(stream_step)>();
+  return op.call(x, hk, tables, xs_in, xs_out, ss_in, ss_out, parity_in, parity_out, flags);
+}
+
 at::Tensor analysis_autograd(const at::Tensor& x, const at::Tensor& hk, const at::Tensor& tables, int64_t n_frames, int64_t flags) {
   return AnalysisFn::apply(x, hk, tables, n_frames, flags);
 }
@@ -433,4 +444,5 @@ TORCH_LIBRARY_IMPL(pqmf_b200, Autograd, m) {
   m.impl("synthesis", &synthesis_autograd);
   m.impl("analysis_stream", &analysis_stream_autograd);
   m.impl("synthesis_stream", &synthesis_stream_autograd);
+  m.impl("stream_step", &stream_step_autograd);
 }

@@ -345,9 +345,6 @@ class CachedPQMF(PQMF):
         updates as the two calls."""
         rows = x.shape[0] * x.shape[1]
         length = self.hk.shape[1]
-        if torch.is_grad_enabled() and x.requires_grad:
-            raise RuntimeError("pqmf_b200 streaming ops are not differentiable (streaming mode carries state across calls); use forward() / "
-                               "inverse() for training or wrap the call in torch.no_grad()")
         if self._x_state.shape[1] != rows or self._x_state.device != x.device:
             self._x_state = torch.zeros(2, rows, length, device=x.device)
             self._x_slot = 0

@@ -167,6 +167,8 @@ def test_stream_ops_refuse_to_be_differentiated(pq):
         y = mod.forward_stream(x)
     with pytest.raises(RuntimeError, match="not differentiable"):
         mod.inverse_stream(y.requires_grad_(True))
+    with pytest.raises(RuntimeError, match="not differentiable"):
+        mod.process_stream(x)
 
 
 @pytest.mark.parametrize("streams,block", ((300, 2048), (4096, 2048), (1000, 512), (97, 7680), (7, 2048), (1, 512)))
