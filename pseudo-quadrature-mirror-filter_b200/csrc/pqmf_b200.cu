@@ -836,11 +836,19 @@ int pqmf_roundtrip_f32(const float* x, float* y, float* out, const float* hk, co
   return pqmf_synthesis_f32(y, out, hk, tables, B, n_frames, M, L, delay_frames, flags, stream);
 }
 
-// rows per chunk of pqmf_reconstruct_f32: the chunk's sub-bands (rows * T * 4 bytes) stay in the 126 MB L2 between the analysis and
-// the synthesis launch, and a chunk is large enough for the tensor-core kernels (>= 96 tiles of 8192 samples) whenever the batch is
+// rows per chunk of pqmf_reconstruct_f32: the chunk's sub-bands (rows * T * 4 bytes, 96 MB by default) are mostly still in the 126 MB L2
+// when the synthesis launch of the chunk reads them, and a chunk is large enough for the tensor-core kernels (>= 96 tiles of 8192
+// samples) whenever the batch is.  Measured at 64 x 2^20 against process() (tools/process_bench.py, sustained / burst): 32 MB chunks
+// -13 % / -38 %, 48 MB -12 % / -27 %, 64 MB -6 % / -22 %, 96 MB -4 % / -13 %, 128 MB -2 % / -10 %: every extra launch pair costs a pipeline
+// fill and drain on all SMs, so the chunk is as large as still saves most of the sub-band tensor (96 MB scratch instead of 268 MB).
 long recon_chunk_rows(int B, long T) {
+  static const long chunk_bytes = [] {
+    const char* e = getenv("PQMF_RECON_CHUNK_MIB");   // tuning knob, read once
+    const long v = e ? atol(e) : 0;
+    return (v > 0 && v <= 4096 ? v : 96L) << 20;
+  }();
   const long row_bytes = T * (long)sizeof(float);
-  long rows = (48L << 20) / (row_bytes > 0 ? row_bytes : 1);
+  long rows = chunk_bytes / (row_bytes > 0 ? row_bytes : 1);
   const long tiles_per_row = (T + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples;
   const long min_rows = (96 + tiles_per_row - 1) / (tiles_per_row > 0 ? tiles_per_row : 1);
   if (rows < min_rows) rows = min_rows;
