@@ -49,7 +49,7 @@ template <int M, bool PAIR>
 __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStreamParams& p, const H4Smem& sm, uint32_t tmem, uint32_t pfull_leader,
                                                            unsigned n_iter, unsigned it0, unsigned bank_phase, int tid) {
   constexpr int FR = 64 / M, HB = M / 2;  // frames per 64-sample row, bands per epilogue thread
-  constexpr int NQ = (kH4Rows * 16 + kH4Workers - 1) / kH4Workers;  // 8 float4 per thread cover the 128 region rows of a tile
+  constexpr int NO = (kH4Rows * 8 + kH4Workers - 1) / kH4Workers;  // 4 x 8 samples per thread cover the 128 region rows of a tile
   const H4Shape& g = p.g;
   const H4StreamGeom& sg = p.s;
   const int warp = tid >> 5;
@@ -57,35 +57,37 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
   for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4Workers)
 #pragma unroll
     for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
-  // tile-invariant map of this thread's quads: region (stream slot) and offset inside the stream's history / block
-  const int region_quads = sg.pitch * 16, n_quads = sg.spt * region_quads;
+  // tile-invariant map of this thread's 8-sample groups: region (stream slot) and offset inside the stream's history / block
+  const int region_octs = sg.pitch * 8, n_octs = sg.spt * region_octs;
   const long F = p.T / M;
-  int q_slot[NQ], q_off[NQ];  // q_off >= 0: sample offset in the block; -1 - h: sample offset h in the history; slot -1: padding (zeros)
+  int q_slot[NO], q_off[NO];  // q_off >= 0: sample offset in the block; -1 - h: sample offset h in the history; slot -1: padding (zeros)
 #pragma unroll
-  for (int r = 0; r < NQ; ++r) {
+  for (int r = 0; r < NO; ++r) {
     const int u = tid + kH4Workers * r;
     q_slot[r] = -1;
     q_off[r] = 0;
-    if (u < n_quads) {
-      const int t = u / region_quads, w = u - t * region_quads, q = w >> 4, col = w & 15;
+    if (u < n_octs) {
+      const int t = u / region_octs, w = u - t * region_octs, q = w >> 3, col = w & 7;
       if (q < sg.hrows) {
         q_slot[r] = t;
-        q_off[r] = -1 - ((p.L - sg.hrows * 64) + q * 64 + 4 * col);
+        q_off[r] = -1 - ((p.L - sg.hrows * 64) + q * 64 + 8 * col);
       } else if (q - sg.hrows < sg.rows_b) {
         q_slot[r] = t;
-        q_off[r] = (q - sg.hrows) * 64 + 4 * col;
+        q_off[r] = (q - sg.hrows) * 64 + 8 * col;
       }
     }
   }
-  float4 xr[NQ];
+  float xr[NO][8];
   auto load_tile = [&](long tile) {
 #pragma unroll
-    for (int r = 0; r < NQ; ++r) {
+    for (int r = 0; r < NO; ++r) {
       const long sidx = tile * sg.spt + q_slot[r];
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q_slot[r] >= 0 && sidx < p.B)
-        v = ptx::ldg128_na(reinterpret_cast<const float4*>(q_off[r] >= 0 ? p.x + (size_t)sidx * p.T + q_off[r] : p.hist_in + (size_t)sidx * p.L + (-1 - q_off[r])));
-      xr[r] = v;
+      if (q_slot[r] >= 0 && sidx < p.B) {
+        ptx::ldg256_na(q_off[r] >= 0 ? p.x + (size_t)sidx * p.T + q_off[r] : p.hist_in + (size_t)sidx * p.L + (-1 - q_off[r]), xr[r]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xr[r][e] = 0.f;
+      }
     }
   };
   // fp32 -> fp16 planes; the threads that hold the last L samples of a block also roll the history (here, where the data is
@@ -94,18 +96,23 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
     unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
     unsigned char* p2 = p1 + g.plane;
 #pragma unroll
-    for (int r = 0; r < NQ; ++r) {
+    for (int r = 0; r < NO; ++r) {
       const int u = tid + kH4Workers * r;
-      if (u < n_quads) {
-        uint2 a, bq;
-        split2_f16s(xr[r].x, xr[r].y, a.x, bq.x);
-        split2_f16s(xr[r].z, xr[r].w, a.y, bq.y);
-        const uint32_t o = sw128_offset((uint32_t)u * 8u);
-        *reinterpret_cast<uint2*>(p1 + o) = a;
-        *reinterpret_cast<uint2*>(p2 + o) = bq;
+      if (u < n_octs) {
+        uint4 a, bq;
+        split2_f16s(xr[r][0], xr[r][1], a.x, bq.x);
+        split2_f16s(xr[r][2], xr[r][3], a.y, bq.y);
+        split2_f16s(xr[r][4], xr[r][5], a.z, bq.z);
+        split2_f16s(xr[r][6], xr[r][7], a.w, bq.w);
+        const uint32_t o = sw128_offset((uint32_t)u * 16u);
+        *reinterpret_cast<uint4*>(p1 + o) = a;
+        *reinterpret_cast<uint4*>(p2 + o) = bq;
         const long sidx = tile * sg.spt + q_slot[r];
-        if (q_slot[r] >= 0 && q_off[r] >= p.T - p.L && sidx < p.B)
-          *reinterpret_cast<float4*>(p.hist_out + (size_t)sidx * p.L + (q_off[r] - (p.T - p.L))) = xr[r];
+        if (q_slot[r] >= 0 && q_off[r] >= p.T - p.L && sidx < p.B) {
+          float* dst = p.hist_out + (size_t)sidx * p.L + (q_off[r] - (p.T - p.L));
+          *reinterpret_cast<float4*>(dst) = make_float4(xr[r][0], xr[r][1], xr[r][2], xr[r][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(xr[r][4], xr[r][5], xr[r][6], xr[r][7]);
+        }
       }
     }
   };

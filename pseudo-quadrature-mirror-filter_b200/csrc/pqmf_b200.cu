@@ -301,7 +301,7 @@ int h4_analysis_stream(const float* x, float* y, const float* tables, const floa
   if (hist > L || T % 256 != 0 || T < L) return PQMF_ERR_UNSUPPORTED;
   const pqmf::H4StreamGeom sg = pqmf::h4_stream_geom(T, hist);
   if (sg.pitch > pqmf::kH4Rows || sg.spt < 1 || (B + sg.spt - 1) / sg.spt < 96) return PQMF_ERR_UNSUPPORTED;
-  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)state_in | (uintptr_t)state_out) % 16) return PQMF_ERR_UNSUPPORTED;
+  if (((uintptr_t)x | (uintptr_t)state_in) % 32 || ((uintptr_t)y | (uintptr_t)state_out) % 16 || L % 8 != 0) return PQMF_ERR_UNSUPPORTED;  // 256-bit loads
   pqmf::H4AnalysisStreamParams p{};
   p.x = x; p.hist_in = state_in; p.hist_out = state_out; p.y = y; p.T = T; p.B = B; p.L = L; p.parity = parity & 1;
   p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);
