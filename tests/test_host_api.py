@@ -174,3 +174,34 @@ def test_tables_exist_for_the_tensor_core_band_counts_and_degrade_gracefully():
     for att, m in ((120, 64), (100, 2)):
         mod = pq.PQMF(att, m)
         assert mod._tables.numel() == 0 and (mod._flags >> 8) == 0
+
+
+def test_cabi_argument_checks_happen_before_any_cuda_call(pq):
+    """Every entry point validates its arguments on the host and returns PQMF_ERR_ARG without touching the device -- so this runs on
+    the CPU box too (no compute calls without a GPU)."""
+    from pqmf_b200 import _lib
+
+    c = _lib.cabi
+    c.pqmf_reconstruct_scratch_bytes.restype = ctypes.c_size_t
+    c.pqmf_reconstruct_scratch_bytes.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int]
+    assert c.pqmf_reconstruct_scratch_bytes(0, 1024, 64, 16) == 0
+    # 64 rows x 2^20: 96 MB chunks = 24 rows of 16 x 65536 floats
+    assert c.pqmf_reconstruct_scratch_bytes(64, 1 << 20, 1 << 16, 16) == 24 * (1 << 20) * 4
+    assert c.pqmf_reconstruct_scratch_bytes(2, 4096, 256, 16) == 2 * 4096 * 4          # a small batch is one chunk
+    c.pqmf_reconstruct_f32.restype = ctypes.c_int
+    c.pqmf_reconstruct_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_size_t] + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_long, ctypes.c_long,
+                                                                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                                                                                    ctypes.c_void_p]
+    assert c.pqmf_reconstruct_f32(None, None, None, 0, None, None, 1, 64, 4, 16, 512, 0, 0, None) == -1
+    assert c.pqmf_reconstruct_f32(None, None, None, 0, None, None, 0, 64, 4, 16, 512, 0, 0, None) == 0       # empty batch
+    assert c.pqmf_analysis_pcm16(None, None, None, None, 1, 64, 2, 0, 4, 16, 512, 0, None) == -1
+    assert c.pqmf_analysis_pcm16(None, None, None, None, 1, 64, 0, 0, 4, 16, 512, 0, None) == -1             # zero channels
+    assert c.pqmf_synthesis_pcm16(None, None, None, None, 1, 1, 4, 16, 512, 3, 0, None) == -1                # bad delay
+    assert c.pqmf_synthesis_bands_f32(None, None, None, None, 1, 4, 16, 512, 1, None, None, None, None, 0, 0, None) == -1
+    assert c.pqmf_stream_step_f32(None, None, None, None, None, None, None, None, None, 1, 2048, 16, 512, 0, 0, 0, None) == -1
+    assert c.pqmf_stream_step_f32(None, None, None, None, None, None, None, None, None, 1, 2049, 16, 512, 0, 0, 0, None) == -1  # T % M != 0
+    devs = (ctypes.c_int * 2)(0, 1)
+    assert c.pqmf_roundtrip_host_multi_f32(None, None, None, None, None, 4, 64, 16, 512, 0, 0, devs, 0) == -1     # no devices
+    assert c.pqmf_roundtrip_host_multi_f32(None, None, None, None, None, 4, 64, 16, 512, 0, 0, devs, 2) == -1     # null buffers
+    assert c.pqmf_roundtrip_host_pcm16(None, None, None, None, None, 4, 64, 0, 16, 512, 0, 0, 0) == -1            # zero channels
+    assert b"invalid argument" in c.pqmf_strerror(-1)
