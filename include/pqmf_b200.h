@@ -199,6 +199,9 @@ int pqmf_roundtrip_host_pcm16(const int16_t* pcm_host, float* y_host, int16_t* o
 int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
                                   const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
                                   const int* devices, int n_devices);
+/* The row range [*start, *start + *count) of shard `shard` of `n_shards` (what pqmf_roundtrip_host_multi_f32 gives device number
+ * `shard` of its list; host-only arithmetic, the same rule as the Python side's shard_rows). */
+void pqmf_shard_rows(long n_rows, int n_shards, int shard, long* start, long* count);
 
 /* Frees the per-device staging buffers / streams that the pqmf_roundtrip_host_* entry points keep between calls. */
 void pqmf_host_release(void);

@@ -890,6 +890,13 @@ int pqmf_roundtrip_host_pcm16(const int16_t* pcm_host, float* y_host, int16_t* o
   return roundtrip_host(pcm_host, y_host, out_host, hk_host, tables_host, B, T, C, M, L, delay_frames, flags, device);
 }
 
+void pqmf_shard_rows(long n_rows, int n_shards, int shard, long* start, long* count) {
+  // contiguous, disjoint, covering; sizes differ by at most one (the same rule as pqmf_b200/sharding.py: shard_rows)
+  const long base = n_shards > 0 ? n_rows / n_shards : 0, extra = n_shards > 0 ? n_rows % n_shards : 0;
+  if (start) *start = (long)shard * base + (shard < extra ? shard : extra);
+  if (count) *count = base + (shard < extra ? 1 : 0);
+}
+
 int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
                                   const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
                                   const int* devices, int n_devices) {
@@ -899,10 +906,9 @@ int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out
   // rows are independent: contiguous shards, sizes differing by at most one, one host thread per device, no collective
   std::vector<std::thread> workers;
   std::vector<int> rcs((size_t)n_devices, PQMF_OK);
-  const long base = B / n_devices, extra = B % n_devices;
-  long r0 = 0;
   for (int i = 0; i < n_devices; ++i) {
-    const long rows = base + (i < extra ? 1 : 0);
+    long r0 = 0, rows = 0;
+    pqmf_shard_rows(B, n_devices, i, &r0, &rows);
     if (rows > 0) {
       const size_t off = (size_t)r0 * T;
       workers.emplace_back([=, &rcs] {
@@ -910,7 +916,6 @@ int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out
                                                  delay_frames, flags, devices[i]);
       });
     }
-    r0 += rows;
   }
   for (auto& w : workers) w.join();
   for (int rc : rcs)

@@ -61,3 +61,23 @@ def test_shard_rows_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_rows(4, 2, 2)
+
+
+def test_c_abi_sharding_rule_equals_the_python_one():
+    """pqmf_roundtrip_host_multi_f32 splits rows with pqmf_shard_rows: the same contiguous split as pqmf_b200.sharding.shard_rows."""
+    import ctypes
+
+    sys.path.insert(0, ROOT)
+    from pqmf_b200 import _lib
+    from pqmf_b200.sharding import shard_rows
+
+    f = _lib.cabi.pqmf_shard_rows
+    f.restype = None
+    f.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_long)]
+    for n in (0, 1, 7, 37, 64, 4096, 16385):
+        for w in (1, 2, 3, 4, 8):
+            for r in range(w):
+                a, c = ctypes.c_long(), ctypes.c_long()
+                f(n, w, r, ctypes.byref(a), ctypes.byref(c))
+                lo, hi = shard_rows(n, w, r)
+                assert (a.value, a.value + c.value) == (lo, hi)
