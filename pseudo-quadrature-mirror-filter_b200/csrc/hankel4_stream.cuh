@@ -57,42 +57,58 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
   for (int u = sg.spt * sg.pitch * 32 + tid; u < g.rows * 32; u += kH4Workers)
 #pragma unroll
     for (int pl = 0; pl < 4; ++pl) reinterpret_cast<float*>(sm.planes + pl * g.plane)[u] = 0.f;
-  // tile-invariant map of this thread's 8-sample groups: region (stream slot) and offset inside the stream's history / block
+  // tile-invariant plan of this thread's 8-sample groups, made once: the stream slot, RUNNING pointers to the group's source (history or
+  // block) and -- for the groups that hold the tail of a block -- to its place in the next history, and what a tile step adds to them.
+  // The loop below then only tests the slot against the live streams of the tile and bumps pointers (no per-tile index arithmetic).
   const int region_octs = sg.pitch * 8, n_octs = sg.spt * region_octs;
   const long F = p.T / M;
-  int q_slot[NO], q_off[NO];  // q_off >= 0: sample offset in the block; -1 - h: sample offset h in the history; slot -1: padding (zeros)
+  const size_t step_x = (size_t)gridDim.x * sg.spt * p.T, step_h = (size_t)gridDim.x * sg.spt * p.L;
+  constexpr int kDead = 1 << 20;  // slot of padding rows: never below the live-stream count
+  int q_slot[NO];
+  const float* src[NO];
+  size_t src_step[NO];
+  float* roll[NO];  // where the group goes in hist_out (nullptr: it is not part of the last L samples)
 #pragma unroll
   for (int r = 0; r < NO; ++r) {
     const int u = tid + kH4Workers * r;
-    q_slot[r] = -1;
-    q_off[r] = 0;
+    q_slot[r] = kDead;
+    src[r] = p.x;
+    src_step[r] = 0;
+    roll[r] = nullptr;
     if (u < n_octs) {
       const int t = u / region_octs, w = u - t * region_octs, q = w >> 3, col = w & 7;
+      const size_t stream0 = (size_t)blockIdx.x * sg.spt + t;  // the stream this group belongs to in this CTA's first tile
       if (q < sg.hrows) {
         q_slot[r] = t;
-        q_off[r] = -1 - ((p.L - sg.hrows * 64) + q * 64 + 8 * col);
+        src[r] = p.hist_in + stream0 * p.L + ((p.L - sg.hrows * 64) + q * 64 + 8 * col);
+        src_step[r] = step_h;
       } else if (q - sg.hrows < sg.rows_b) {
+        const long off = (q - sg.hrows) * 64 + 8 * col;
         q_slot[r] = t;
-        q_off[r] = (q - sg.hrows) * 64 + 8 * col;
+        src[r] = p.x + stream0 * p.T + off;
+        src_step[r] = step_x;
+        if (off >= p.T - p.L) roll[r] = p.hist_out + stream0 * p.L + (off - (p.T - p.L));
       }
     }
   }
   float xr[NO][8];
+  int nlive = 0;  // live streams of the tile held in xr
   auto load_tile = [&](long tile) {
+    nlive = (int)min((long)sg.spt, (long)p.B - tile * sg.spt);
 #pragma unroll
     for (int r = 0; r < NO; ++r) {
-      const long sidx = tile * sg.spt + q_slot[r];
-      if (q_slot[r] >= 0 && sidx < p.B) {
-        ptx::ldg256_na(q_off[r] >= 0 ? p.x + (size_t)sidx * p.T + q_off[r] : p.hist_in + (size_t)sidx * p.L + (-1 - q_off[r]), xr[r]);
+      if (q_slot[r] < nlive) {
+        ptx::ldg256_na(src[r], xr[r]);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) xr[r][e] = 0.f;
       }
+      src[r] += src_step[r];
     }
   };
   // fp32 -> fp16 planes; the threads that hold the last L samples of a block also roll the history (here, where the data is
   // needed anyway: a store next to the load would make every prefetch wait for its own data)
-  auto convert = [&](int pb, long tile) {
+  auto convert = [&](int pb) {
     unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
     unsigned char* p2 = p1 + g.plane;
 #pragma unroll
@@ -107,11 +123,12 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
         const uint32_t o = sw128_offset((uint32_t)u * 16u);
         *reinterpret_cast<uint4*>(p1 + o) = a;
         *reinterpret_cast<uint4*>(p2 + o) = bq;
-        const long sidx = tile * sg.spt + q_slot[r];
-        if (q_slot[r] >= 0 && q_off[r] >= p.T - p.L && sidx < p.B) {
-          float* dst = p.hist_out + (size_t)sidx * p.L + (q_off[r] - (p.T - p.L));
-          *reinterpret_cast<float4*>(dst) = make_float4(xr[r][0], xr[r][1], xr[r][2], xr[r][3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(xr[r][4], xr[r][5], xr[r][6], xr[r][7]);
+        if (roll[r] != nullptr) {
+          if (q_slot[r] < nlive) {
+            *reinterpret_cast<float4*>(roll[r]) = make_float4(xr[r][0], xr[r][1], xr[r][2], xr[r][3]);
+            *reinterpret_cast<float4*>(roll[r] + 4) = make_float4(xr[r][4], xr[r][5], xr[r][6], xr[r][7]);
+          }
+          roll[r] += step_h;
         }
       }
     }
@@ -120,8 +137,9 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
   const int i = tid & 127, hb = tid >> 7;
   const int et = i / sg.pitch, eq = i - et * sg.pitch;
   const bool e_row = et < sg.spt && eq < sg.rows_b;
+  float* yrun = p.y + (((size_t)blockIdx.x * sg.spt + et) * M + HB * hb) * F + FR * eq;  // this thread's rows of the CTA's first tile
+  const size_t y_step = (size_t)gridDim.x * sg.spt * M * F;
   auto epilogue = [&](long tile, int dbuf) {
-    const long sidx = tile * sg.spt + et;
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + HB * hb);
     uint32_t r0[FR][HB], r1[FR][HB];
 #pragma unroll
@@ -130,8 +148,9 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
       h4_tmem_ld<HB>(taddr + 64 + dl * M, r1[dl]);
     }
     ptx::tmem_ld_wait();
-    if (!e_row || sidx >= p.B) return;
-    float* yp = p.y + ((size_t)sidx * M + HB * hb) * F + FR * eq;
+    float* yp = yrun;
+    yrun += y_step;
+    if (!e_row || tile * sg.spt + et >= p.B) return;
 #pragma unroll
     for (int kk = 0; kk < HB; ++kk) {
       float w[FR];
@@ -159,7 +178,7 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
   long prev_tile = 0;
   for (unsigned it = it0; it < it0 + n_iter; ++it) {
     const int pb = (int)(it & 1);
-    convert(pb, tile);
+    convert(pb);
     h4_publish<PAIR>(sm, pfull_leader, it, pb, tid, it0, bank_phase);
     if (it + 1 < it0 + n_iter) load_tile(tile + gridDim.x);
     if (it > it0) {
@@ -231,36 +250,53 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
   const bool has_item = tid < NBG * n_fq;
   const int region_frames = sg.pitch * FR, hist_fr = sg.hrows * FR, block_fr = sg.rows_b * FR;
   const int lt = (4 * wq) / region_frames, lf = 4 * wq - lt * region_frames;  // region, first frame of the quad within the region
+  const int fb = lf - hist_fr;  // first frame of this thread's quad within the block (negative: history)
+  // tile-invariant plan, made once: RUNNING pointers to the quad's eight band rows (in the state for history frames, in s for block
+  // frames), to its place in the next state when it is one of the block's last K frames, and what a tile step adds to them
+  constexpr int kDead = 1 << 20;
+  const size_t band0 = ((size_t)blockIdx.x * sg.spt + lt) * M + 8 * bg;  // first band row of the item in this CTA's first tile
+  const size_t step_state = (size_t)gridDim.x * sg.spt * M * p.K;
+  int slot = kDead;
+  const float* src = p.s;
+  size_t src_step = 0, src_pitch = 0;
+  float* roll = nullptr;
+  if (has_item) {
+    if (fb < 0) {
+      slot = lt;
+      src = p.state_in + band0 * p.K + (p.K - hist_fr) + lf;
+      src_step = step_state;
+      src_pitch = (size_t)p.K;
+    } else if (fb < block_fr) {
+      slot = lt;
+      src = p.s + band0 * p.F + fb;
+      src_step = (size_t)gridDim.x * sg.spt * M * p.F;
+      src_pitch = (size_t)p.F;
+      if (fb >= p.F - p.K) roll = p.state_out + band0 * p.K + (fb - (p.F - p.K));  // the last K frames of the block become the next history
+    }
+  }
   float4 v[8];
+  int nlive = 0;  // live streams of the tile held in v
   auto load_tile = [&](long tile) {
-    const long sidx = tile * sg.spt + lt;
-    const bool live = has_item && sidx < p.B;
+    nlive = (int)min((long)sg.spt, (long)p.B - tile * sg.spt);
+    const bool live = slot < nlive;
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      const size_t band = (size_t)sidx * M + 8 * bg + kk;
-      if (live) {
-        if (lf < hist_fr) {
-          t = ptx::ldg128_na(reinterpret_cast<const float4*>(p.state_in + band * p.K + (p.K - hist_fr) + lf));
-        } else if (lf - hist_fr < block_fr) {
-          const float4* src = reinterpret_cast<const float4*>(p.s + band * p.F + (lf - hist_fr));
-          t = OWN ? ptx::ldg128_cg(src) : ptx::ldg128_na(src);
-        }
-      }
-      v[kk] = t;
+      const float4* q = reinterpret_cast<const float4*>(src + (size_t)kk * src_pitch);
+      v[kk] = live ? (OWN ? ptx::ldg128_cg(q) : ptx::ldg128_na(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    src += src_step;
   };
   // sigma(k, n): odd bands flip on even global frames; regions and history lengths are multiples of 4 frames, so the parity is j's
   const uint32_t flip_even = (p.parity & 1) ? 0u : 0x80000000u, flip_odd = flip_even ^ 0x80000000u;
-  const int fb = lf - hist_fr;  // first frame of this thread's quad within the block (negative: history)
-  auto convert = [&](int pb, long tile) {
+  auto convert = [&](int pb) {
     if (!has_item) return;
     unsigned char* p1 = sm.planes + (2 * pb) * g.plane;
-    const long sidx = tile * sg.spt + lt;
-    if (fb >= p.F - p.K && fb < block_fr && sidx < p.B) {  // the last K frames of the block become the next history
+    if (roll != nullptr) {
+      if (slot < nlive) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        *reinterpret_cast<float4*>(p.state_out + ((size_t)sidx * M + 8 * bg + kk) * p.K + (fb - (p.F - p.K))) = v[kk];
+        for (int kk = 0; kk < 8; ++kk) *reinterpret_cast<float4*>(roll + (size_t)kk * p.K) = v[kk];
+      }
+      roll += step_state;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -286,8 +322,9 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
   const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
   const int i0 = i & ~3, et = i0 / sg.pitch, eq0 = i0 - et * sg.pitch;
   const bool e_rows = et < sg.spt && eq0 < sg.rows_b;
+  float* orun = p.out + ((size_t)blockIdx.x * sg.spt + et) * (size_t)(p.F * M) + 64 * eq0 + 32 * hb + 8 * (lane & 3);  // slot q: row eq0 + q of the block
+  const size_t out_step = (size_t)gridDim.x * sg.spt * (size_t)(p.F * M);
   auto epilogue = [&](long tile, int dbuf) {
-    const long sidx = tile * sg.spt + et;
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
     uint32_t r0[2][16], r1[2][16];
     ptx::tmem_ld16(taddr, r0[0]);
@@ -317,8 +354,9 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
         val[u + 2][e] = b1 ? val[u + 2][e] : recv;
         val[u][e] = b1 ? recv : val[u][e];
       }
-    if (!e_rows || sidx >= p.B) return;
-    float* op = p.out + (size_t)sidx * (p.F * M) + 64 * eq0 + 32 * hb + 8 * (lane & 3);  // slot q: row eq0 + q of the block
+    float* op = orun;
+    orun += out_step;
+    if (!e_rows || tile * sg.spt + et >= p.B) return;
 #pragma unroll
     for (int q = 0; q < 4; ++q) ptx::stg256_cs(op + (size_t)q * 64, val[q]);
   };
@@ -328,7 +366,7 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
   long prev_tile = 0;
   for (unsigned it = it0; it < it0 + n_iter; ++it) {
     const int pb = (int)(it & 1);
-    convert(pb, tile);
+    convert(pb);
     h4_publish<PAIR>(sm, pfull_leader, it, pb, tid, it0, bank_phase);
     if (it + 1 < it0 + n_iter) load_tile(tile + gridDim.x);
     if (it > it0) {
