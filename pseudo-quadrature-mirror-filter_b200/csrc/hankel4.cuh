@@ -457,6 +457,8 @@ struct H4SynthesisParams {
   float* out;            // [B, M F]
   int16_t* pcm_out;      // PCM instantiation: interleaved int16 WAV frames [B / C, M F, C] (out unused)
   int C;
+  int duo;               // PCM stereo: the launch walks CLIPS; a CTA runs the left and the right row of a tile back to back and its
+                         // epilogue threads -- which hold the same eight samples of both -- store whole interleaved 32-byte groups
   const uint16_t* bank;
   long F;
   int o;                 // off2 / M: L / (2 M) (PQMF.inverse) or one less (CachedPQMF.inverse)
@@ -489,7 +491,8 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
   const unsigned step_b = gridDim.x / tpr, step_c = gridDim.x % tpr;
   unsigned b = blockIdx.x / tpr, c = blockIdx.x % tpr;
   const unsigned first_tile = PAIR ? (blockIdx.x & ~1u) : blockIdx.x;
-  const unsigned n_iter = (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
+  const unsigned G = (PCM && p.duo) ? 2u : 1u;  // rows per tile visit (see H4SynthesisParams::duo): b counts clips then, row = G b + channel
+  const unsigned n_iter = G * (unsigned)((p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
   const unsigned n_rows = (unsigned)(p.n_tiles / p.tiles_per_row);
 
   // plane frame m <-> sub-band frame n = 128 FR c + (o - ehi - pad) + m, ehi = largest frame lag with a non-zero tap,
@@ -508,20 +511,21 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     const int bg = tid / n_fq, fq = tid - bg * n_fq;
     const bool has_item = tid < n_fq * NBG;
     float4 v0[8];  // prefetched one tile ahead
-    auto load_frames = [&](float4 (&v)[8], unsigned bb, unsigned cc) {
+    auto load_frames = [&](float4 (&v)[8], unsigned bb, unsigned cc, unsigned hh) {
       if (p.reverse && bb < n_rows) {
         bb = n_rows - 1 - bb;
         cc = tpr - 1 - cc;
       }
       const long n = (long)cc * (kH4Rows * FR) + nbase + FPI * fq;
       const bool live = bb < n_rows && has_item;
+      const size_t row = (size_t)bb * G + hh;
       if constexpr (M >= 8) {  // v[kk] = frames n .. n + 3 of band 8 bg + kk
-        const float* sp = p.s + ((size_t)bb * M + 8 * bg) * p.F + n;
+        const float* sp = p.s + (row * M + 8 * bg) * p.F + n;
         const bool ok = live && n >= 0 && n + 3 < p.F;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) v[kk] = ok ? ptx::ldg128_na(reinterpret_cast<const float4*>(sp + (size_t)kk * p.F)) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {                 // n_band 4: v[2 b + h] = frames n + 4 h .. n + 4 h + 3 of band b
-        const float* sp = p.s + (size_t)bb * M * p.F + n;
+        const float* sp = p.s + row * M * p.F + n;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const int b4 = kk >> 1, h = kk & 1;
@@ -577,11 +581,13 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
     // D (TMEM) -> out.  Thread (row i, half hb) drains 32 consecutive output samples = four 32-byte chunks, but rows are 256 B
     // apart: stored like that, every warp store would touch 32 lines.  A 4 x 4 chunk transpose inside each lane quad (two shuffle
     // stages) leaves lane r with chunk r & 3 of the quad's four rows, so one STG.256 covers eight whole 128-byte lines.
-    auto epilogue = [&](unsigned bb, unsigned cc, int dbuf) {
+    uint32_t held[4][4];  // duo: the left channel's quantised samples of this thread's four chunks, kept for the right channel's visit
+    auto epilogue = [&](unsigned bb, unsigned cc, unsigned hh, int dbuf) {
       if (p.reverse) {
         bb = n_rows - 1 - bb;
         cc = tpr - 1 - cc;
       }
+      const size_t row = (size_t)bb * G + hh;
       const int i = tid & 127, hb = tid >> 7, lane = tid & 31;
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dbuf * 128 + 2 * hb * 16);
       uint32_t r0[2][16], r1[2][16];
@@ -616,12 +622,34 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
       const long total = p.F * M;  // samples per output row (a multiple of 8: the dispatcher requires F % 4 == 0)
       const long t0 = (long)cc * kH4TileSamples + 64 * (i & ~3) + 32 * hb + 8 * (lane & 3);
       if constexpr (PCM) {
+        if (G == 2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              w[k] = (uint32_t)(uint16_t)pcm_quantise(val[q][2 * k]) | ((uint32_t)(uint16_t)pcm_quantise(val[q][2 * k + 1]) << 16);
+            if (hh == 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) held[q][k] = w[k];
+            } else if (t0 + 64 * q + 7 < total) {
+              float lr[8];  // eight WAV frames (left | right << 16) as raw words
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                lr[2 * k] = __uint_as_float(__byte_perm(held[q][k], w[k], 0x5410));
+                lr[2 * k + 1] = __uint_as_float(__byte_perm(held[q][k], w[k], 0x7632));
+              }
+              ptx::stg256_cs(reinterpret_cast<float*>(p.pcm_out + ((size_t)bb * total + t0 + 64 * q) * 2), lr);
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (t0 + 64 * q + 7 < total) pcm_store8(p.pcm_out, p.C, bb, t0 + 64 * q, total, val[q]);
+          if (t0 + 64 * q + 7 < total) pcm_store8(p.pcm_out, p.C, (long)row, t0 + 64 * q, total, val[q]);
         return;
       }
-      float* op = p.out + (size_t)bb * total + t0;
+      float* op = p.out + row * total + t0;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (t0 + 64 * q + 7 < total) {
@@ -635,34 +663,42 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
         }
     };
 
-    unsigned b1 = b, c1 = c;
-    advance(b1, c1);
-    load_frames(v0, b, c);
-    unsigned prev_b = 0, prev_c = 0;
+    auto next_visit = [&](unsigned& bb, unsigned& cc, unsigned& hh) {  // the tile's next row, or the CTA's next tile
+      if (++hh == G) {
+        hh = 0;
+        advance(bb, cc);
+      }
+    };
+    unsigned h = 0, b1 = b, c1 = c, h1 = 0;
+    next_visit(b1, c1, h1);
+    load_frames(v0, b, c, h);
+    unsigned prev_b = 0, prev_c = 0, prev_h = 0;
     for (unsigned it = 0; it < n_iter; ++it) {
       const int pb = (int)(it & 1);
       H4_STAMP(0);
       convert(v0, pb);
       H4_STAMP(1);
       h4_publish<PAIR>(sm, pfull_leader, it, pb, tid);
-      if (it + 1 < n_iter) load_frames(v0, b1, c1);
+      if (it + 1 < n_iter) load_frames(v0, b1, c1, h1);
       H4_STAMP(2);
       if (it > 0) {
         // every worker waits (planes[pb ^ 1] are rewritten next iteration); the ninth warp has no TMEM rows to drain
         ptx::mbar_wait(&sm.mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
         ptx::tc_fence_after();
-        if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((it - 1) & 1));
+        if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, prev_h, (int)((it - 1) & 1));
       }
       H4_STAMP(5);
       prev_b = b;
       prev_c = c;
+      prev_h = h;
       b = b1;
       c = c1;
-      advance(b1, c1);
+      h = h1;
+      next_visit(b1, c1, h1);
     }
     ptx::mbar_wait(&sm.mma_bar[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
     ptx::tc_fence_after();
-    if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, (int)((n_iter - 1) & 1));
+    if (warp < 8 && prev_b < n_rows) epilogue(prev_b, prev_c, prev_h, (int)((n_iter - 1) & 1));
   }  // workers
   h4_teardown<PAIR>(tmem, warp);
 }
@@ -753,8 +789,12 @@ template <int M, bool PAIR>
 int h4_launch_synthesis(H4SynthesisParams p, int B, cudaStream_t st) {
   static H4Configured configured[2];
   if (p.pcm_out != nullptr) {
-    if constexpr (PAIR) return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR, true>, p, B, p.F * M, kH4SynThreads, configured[1], st);
-    else return -2;
+    if constexpr (PAIR) {
+      p.duo = (p.C == 2 && B % 2 == 0) ? 1 : 0;  // stereo: the tiles of a launch are (clip, chunk), each visited once per channel
+      return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR, true>, p, p.duo ? B / 2 : B, p.F * M, kH4SynThreads, configured[1], st);
+    } else {
+      return -2;
+    }
   }
   return h4_launch<PAIR>(h4_synthesis_kernel<M, PAIR, false>, p, B, p.F * M, kH4SynThreads, configured[0], st);
 }
