@@ -57,7 +57,9 @@ def test_analysis_from_pcm_is_bit_identical_to_the_float_path(pq, m, b, t, c):
 
 
 @pytest.mark.parametrize("m,b,f,c", ((16, 2, 256, 1), (16, 3, 128, 2), (16, 24, 2048, 1), (16, 12, 2048, 2), (8, 24, 4096, 1), (32, 24, 1024, 1),
-                                     (64, 24, 512, 1), (16, 2, 2048, 5)))
+                                     (64, 24, 512, 1), (16, 2, 2048, 5),
+                                     # stereo on the Hankel kernels: several (left, right) visits per CTA, odd clip counts, partial last tiles
+                                     (16, 101, 2560, 2), (8, 37, 5000, 2), (32, 40, 1280, 2), (4, 33, 6144, 2), (16, 7, 65536, 2)))
 def test_synthesis_to_pcm_quantises_like_torch(pq, m, b, f, c):
     torch.manual_seed(m + f + c)
     mod = pq.CachedPQMF(100, m).cuda()
