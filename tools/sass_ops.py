@@ -13,7 +13,7 @@ LIB = os.path.join(ROOT, "pseudo-quadrature-mirror-filter_b200", "libpqmf_b200.s
 
 
 def main():
-    want = sys.argv[1:] or ["h4_analysis_kernel<(int)16, (bool)1", "h4_synthesis_kernel<(int)16, (bool)1", "h4_analysis_stream", "h4_synthesis_stream", "stream_step"]
+    want = sys.argv[1:] or ["h4_analysis_kernel<(int)16, (bool)1", "h4_synthesis_kernel<(int)16, (bool)1", "h4_analysis_stream", "h4_synthesis_stream", "f16_"]
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     names = {}
     funcs = re.split(r"\n\s*Function : ", sass)[1:]
@@ -31,7 +31,8 @@ def main():
                 if mm.group(1) in ("UTCHMMA", "LDTM", "UBLKCP", "STG", "LDG", "STS", "LDS", "SYNCS", "UTCBAR", "F2FP", "FFMA2", "FMUL2", "SHFL"):
                     full[mm.group(1) + mm.group(2)] += 1
         total = sum(ops.values())
-        print(f"== {d.split('(')[0]}   [{total} instructions]")
+        name = d[:d.index(">(") + 1] if ">(" in d else d.split("(")[0]
+        print(f"== {name}   [{total} instructions]")
         print("   " + "  ".join(f"{k}:{v}" for k, v in ops.most_common(28)))
         print("   detail: " + "  ".join(f"{k}:{v}" for k, v in sorted(full.items())))
     return 0
