@@ -132,6 +132,15 @@ __device__ __forceinline__ float h4_combine(uint32_t d0, uint32_t d1) {
   return fmaf(__uint_as_float(d1), 1.0f / kH4Res, __uint_as_float(d0)) * (1.0f / (float)(1 << kH16ScaleLog2));
 }
 
+// the same for two adjacent columns as packed FP32 (one FFMA2 + one FMUL2 instead of two of each: the epilogue sits on the workers'
+// critical path); per element exactly the arithmetic of h4_combine
+__device__ __forceinline__ float2 h4_combine2(uint32_t d0a, uint32_t d0b, uint32_t d1a, uint32_t d1b) {
+  const float2 t = __ffma2_rn(make_float2(__uint_as_float(d1a), __uint_as_float(d1b)), make_float2(1.0f / kH4Res, 1.0f / kH4Res),
+                              make_float2(__uint_as_float(d0a), __uint_as_float(d0b)));
+  constexpr float kInv = 1.0f / (float)(1 << kH16ScaleLog2);
+  return __fmul2_rn(t, make_float2(kInv, kInv));
+}
+
 template <int N>
 __device__ __forceinline__ void h4_tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
   static_assert(N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "columns per load");
@@ -366,9 +375,10 @@ __global__ void __launch_bounds__(kH4Threads, 1) h4_analysis_kernel(H4AnalysisPa
         // sigma(k, n): odd bands flip on even frames; n (a multiple of FR) is even for FR > 1, so the frame parity is dl's
         const uint32_t flip = (((FR > 1 ? dl : (int)(n & 1)) + p.parity) & 1) == 0 ? 0x80000000u : 0u;
 #pragma unroll
-        for (int kk = 0; kk < HB; ++kk) {
-          const float t = h4_combine(r0[dl][kk], r1[dl][kk]);
-          v[dl][kk] = __uint_as_float(__float_as_uint(t) ^ ((kk & 1) ? flip : 0u));
+        for (int kk = 0; kk < HB; kk += 2) {
+          const float2 t = h4_combine2(r0[dl][kk], r0[dl][kk + 1], r1[dl][kk], r1[dl][kk + 1]);
+          v[dl][kk] = t.x;
+          v[dl][kk + 1] = __uint_as_float(__float_as_uint(t.y) ^ flip);
         }
       }
       float* yp = p.y + ((size_t)bb * M + HB * hb) * p.F + n;
@@ -600,7 +610,12 @@ __global__ void __launch_bounds__(kH4SynThreads, 1) h4_synthesis_kernel(H4Synthe
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) val[q][e] = h4_combine(r0[q >> 1][8 * (q & 1) + e], r1[q >> 1][8 * (q & 1) + e]);
+        for (int e = 0; e < 8; e += 2) {
+          const int c0 = 8 * (q & 1) + e;
+          const float2 t = h4_combine2(r0[q >> 1][c0], r0[q >> 1][c0 + 1], r1[q >> 1][c0], r1[q >> 1][c0 + 1]);
+          val[q][e] = t.x;
+          val[q][e + 1] = t.y;
+        }
       const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr)  // lanes r, r ^ 1 swap the off-diagonal chunks of (2 pr, 2 pr + 1)

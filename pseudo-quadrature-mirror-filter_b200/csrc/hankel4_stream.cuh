@@ -151,16 +151,23 @@ __device__ __forceinline__ void h4_analysis_stream_workers(const H4AnalysisStrea
     float* yp = yrun;
     yrun += y_step;
     if (!e_row || tile * sg.spt + et >= p.B) return;
+    float v[FR][HB];
+#pragma unroll
+    for (int dl = 0; dl < FR; ++dl) {
+      // global frame parity = parity of (FR eq + dl) + frame_parity; FR eq is even for FR > 1: odd bands flip on even frames
+      const uint32_t flip = ((((FR > 1 ? dl : eq) + p.parity) & 1) == 0) ? 0x80000000u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < HB; kk += 2) {
+        const float2 t = h4_combine2(r0[dl][kk], r0[dl][kk + 1], r1[dl][kk], r1[dl][kk + 1]);
+        v[dl][kk] = t.x;
+        v[dl][kk + 1] = __uint_as_float(__float_as_uint(t.y) ^ flip);
+      }
+    }
 #pragma unroll
     for (int kk = 0; kk < HB; ++kk) {
       float w[FR];
 #pragma unroll
-      for (int dl = 0; dl < FR; ++dl) {
-        // global frame parity = parity of (FR eq + dl) + frame_parity; FR eq is even for FR > 1
-        const int fpar = (FR > 1 ? dl : eq) + p.parity;
-        const uint32_t flip = ((fpar & 1) == 0 && (kk & 1)) ? 0x80000000u : 0u;
-        w[dl] = __uint_as_float(__float_as_uint(h4_combine(r0[dl][kk], r1[dl][kk])) ^ flip);
-      }
+      for (int dl = 0; dl < FR; ++dl) w[dl] = v[dl][kk];
       float* q = yp + (size_t)kk * F;
       if constexpr (FR >= 4) {
 #pragma unroll
@@ -336,7 +343,12 @@ __device__ __forceinline__ void h4_synthesis_stream_workers(const H4SynthesisStr
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) val[q][e] = h4_combine(r0[q >> 1][8 * (q & 1) + e], r1[q >> 1][8 * (q & 1) + e]);
+      for (int e = 0; e < 8; e += 2) {
+        const int c0 = 8 * (q & 1) + e;
+        const float2 t = h4_combine2(r0[q >> 1][c0], r0[q >> 1][c0 + 1], r1[q >> 1][c0], r1[q >> 1][c0 + 1]);
+        val[q][e] = t.x;
+        val[q][e + 1] = t.y;
+      }
     const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr)
