@@ -35,7 +35,10 @@ def _as_float_rows(pcm):
 
 # small shapes run the direct form, >= 96 tiles of 8192 samples the tensor-core Hankel kernels
 @pytest.mark.parametrize("m,b,t,c", ((16, 2, 4096, 1), (16, 3, 2048, 2), (8, 2, 4000, 3), (16, 24, 32768, 1), (16, 12, 32768, 2), (8, 24, 32768, 1),
-                                     (32, 12, 65536, 2), (64, 24, 32768, 1), (4, 25, 32768, 1), (16, 4, 32768, 6)))
+                                     (32, 12, 65536, 2), (64, 24, 32768, 1), (4, 25, 32768, 1), (16, 4, 32768, 6),
+                                     # stereo on the Hankel kernels (a CTA loads a tile's frames once and visits both channels): several
+                                     # visits per CTA, odd clip counts, partial last tiles
+                                     (16, 101, 40960, 2), (8, 37, 40000, 2), (32, 40, 40960, 2), (4, 33, 24576, 2), (16, 7, 1048576, 2)))
 def test_analysis_from_pcm_is_bit_identical_to_the_float_path(pq, m, b, t, c):
     mod = pq.PQMF(100, m).cuda()
     plain = pq.PQMF(100, m, fp32=True).cuda()
