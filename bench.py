@@ -339,7 +339,7 @@ def run_gpu(args):
                    "round_trip_snr_db": round(snr_db, 2)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 4, "d2h_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 4,
-                "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "api": "pqmf_roundtrip_host_f32 (C ABI, pinned host buffers, 16 MiB row chunks on 4 streams)"},
+                "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "api": "pqmf_roundtrip_host_f32 (C ABI, pinned host buffers, 8 MiB row chunks, 4 in flight, copy and kernel streams)"},
         "e2e_pcm16": {"value": round(pcm_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 2, "d2h_bytes_per_step": n_gpus * BATCH * N_SAMPLES * 2,
                       "ms_per_step": round(pcm_ms, 3), "steps": e2e_steps, "api": "pqmf_roundtrip_host_pcm16 (int16 WAV frames in pinned host memory in and out; "
                       "second number beside the fp32 headline)"},

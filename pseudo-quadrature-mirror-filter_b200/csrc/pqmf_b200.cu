@@ -117,10 +117,13 @@ bool bad_dims(int B, long n, int M, int L) { return B < 0 || n < 0 || M < 2 || L
 
 // per-device staging workspace of the host-buffer entry points (pqmf_roundtrip_host_*).  One mutex PER DEVICE: calls for different
 // devices run concurrently (pqmf_roundtrip_host_multi_f32 drives every GPU of the box from one process, one host thread each).
-constexpr int kHostSlots = 4, kMaxDevices = 16;
+constexpr int kHostSlots = 8, kMaxDevices = 16;  // upper bound; the calls cycle through n_slots of them (roundtrip_host)
 struct HostWorkspace {
   std::mutex mutex;
-  cudaStream_t st[kHostSlots] = {};
+  cudaStream_t st[kHostSlots] = {};    // copy streams
+  cudaStream_t kst[kHostSlots] = {};   // kernel streams
+  cudaEvent_t up[kHostSlots] = {}, kdone[kHostSlots] = {}, down[kHostSlots] = {};  // H2D landed / kernels finished / D2H finished, per slot
+  cudaEvent_t bank_up = nullptr;       // this call's bank and tables have landed
   void* d_x[kHostSlots] = {};   // input chunk (fp32 rows or int16 WAV frames)
   float* d_y[kHostSlots] = {};  // sub-bands of the chunk
   void* d_o[kHostSlots] = {};   // output chunk
@@ -415,8 +418,9 @@ bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
 }
 
 // ---- host-buffer round trip, generic over the sample format (float rows, or int16 interleaved WAV frames with C channels) ----
-// Row chunks of ~16 MiB of fp32 samples: H2D(i+1), the two kernels of chunk i and D2H(i-1) overlap (PCIe is full duplex), each chunk
-// on its own stream.  The staging buffers live in a per-device workspace that is created on first use and only ever grows, so
+// Row chunks of ~8 MiB of fp32 samples (2 Mi samples): the H2D copy of chunk i + 1, the two kernels of chunk i and the D2H copy of
+// chunk i - 1 overlap (PCIe is full duplex); copies and kernels have streams of their own (see the copy-phase note in the loop below).
+// The staging buffers live in a per-device workspace that is created on first use and only ever grows, so
 // steady-state calls do no allocation.
 template <typename Sample>
 int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const float* hk_host, const float* tables_host, int B, long T, int C,
@@ -430,9 +434,14 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   if (e != cudaSuccess) return (int)e;
   const long F = T / M;
   static const long chunk_bytes = [] {
-    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 16 MiB of fp32 samples per chunk
+    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 8 MiB of fp32 samples per chunk
     const long v = e ? atol(e) : 0;
-    return (v > 0 && v <= 1024 ? v : 16L) << 20;
+    return (v > 0 && v <= 1024 ? v : 8L) << 20;
+  }();
+  static const int n_slots = [] {
+    const char* e = getenv("PQMF_HOST_SLOTS");       // tuning knob: chunks in flight (default 4)
+    const int v = e ? atoi(e) : 0;
+    return v >= 2 && v <= kHostSlots ? v : 4;
   }();
   const long clip_samples = T * C;                      // one clip = C rows of T samples
   long clips_per_chunk = chunk_bytes / (clip_samples * (long)sizeof(float));
@@ -445,7 +454,14 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   int rc = PQMF_OK;
   auto check = [&](cudaError_t err) { if (err != cudaSuccess && rc == PQMF_OK) rc = (int)err; return err == cudaSuccess; };
   if (!ws.streams_ready) {
-    for (int i = 0; i < kHostSlots; ++i) check(cudaStreamCreateWithFlags(&ws.st[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kHostSlots; ++i) {
+      check(cudaStreamCreateWithFlags(&ws.st[i], cudaStreamNonBlocking));
+      check(cudaStreamCreateWithFlags(&ws.kst[i], cudaStreamNonBlocking));
+      check(cudaEventCreateWithFlags(&ws.up[i], cudaEventDisableTiming));
+      check(cudaEventCreateWithFlags(&ws.kdone[i], cudaEventDisableTiming));
+      check(cudaEventCreateWithFlags(&ws.down[i], cudaEventDisableTiming));
+    }
+    check(cudaEventCreateWithFlags(&ws.bank_up, cudaEventDisableTiming));
     ws.streams_ready = (rc == PQMF_OK);
   }
   if (rc == PQMF_OK && ws.chunk_elems < chunk_elems) {   // buffers are sized for fp32 samples: int16 chunks fit too
@@ -455,6 +471,7 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
       if (ws.d_o[i]) cudaFree(ws.d_o[i]);
       ws.d_x[i] = ws.d_o[i] = nullptr;
       ws.d_y[i] = nullptr;
+      if (i >= n_slots) continue;
       check(cudaMalloc(&ws.d_x[i], chunk_elems * sizeof(float)));
       check(cudaMalloc(&ws.d_y[i], chunk_elems * sizeof(float)));
       check(cudaMalloc(&ws.d_o[i], chunk_elems * sizeof(float)));
@@ -474,12 +491,33 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   // the bank is tiny (<= a few hundred KB): re-send it with every call instead of tracking caller-side changes
   check(cudaMemcpyAsync(d_hk, hk_host, bank_elems * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
   if (n_tab) check(cudaMemcpyAsync(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
-  check(cudaStreamSynchronize(ws.st[0]));
+  check(cudaEventRecord(ws.bank_up, ws.st[0]));
+  for (int i = 0; i < n_slots; ++i) check(cudaStreamWaitEvent(ws.kst[i], ws.bank_up, 0));  // no host-side wait: the first H2D copy follows at once
   // Chunk schedule: small chunks at both ends (1/4, 1/4, 1/2 of a chunk ...) shorten the pipeline fill (nothing overlaps the first
   // H2D) and drain (nothing overlaps the last D2H); full chunks in between keep the kernels efficient.
+  // Copy phase: WHEN a D2H copy starts relative to the H2D copy running beside it decides what both directions get.  With the same
+  // sixteen 16 MiB copies each way and only a delay between a chunk's H2D and its D2H (tools/e2e_pipeline_probe.py), a round trip takes
+  // 5.87 ms at delay 0, 6.3 - 6.7 ms when the D2H starts 5 - 65 % into the next H2D copy, ~6.0 ms at 80 - 95 % and 6.2 - 6.8 ms again
+  // from 100 % on.  A chunk's own D2H, issued behind its kernels, starts a kernel pair's latency (~30 us = 10 %) into the next H2D:
+  // the bad zone.  So the copies get streams of their own in which the D2H of chunk i - 1 directly follows the H2D of chunk i (it starts
+  // the instant that copy ends, i.e. together with the H2D of chunk i + 1), and the kernels run on separate streams, tied in by events:
+  //   copy stream of chunk i  :  [kernels(i - n_slots) done]  H2D(i)  ->up(i)   [kernels(i - 1) done]  D2H(i - 1)  ->down(i - 1)
+  //   kernel stream of chunk i:  [up(i)]  [down(i - n_slots)]  analysis(i), synthesis(i)  ->kdone(i)
+  struct Pending {
+    bool live = false;
+    int slot = 0;
+    long r0 = 0;
+    size_t n = 0;
+  } prev;
+  auto copy_out = [&](const Pending& c, cudaStream_t s) {  // sub-bands and output of chunk c back to the host, once its kernels are done
+    check(cudaStreamWaitEvent(s, ws.kdone[c.slot], 0));
+    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)c.r0 * clip_samples, ws.d_y[c.slot], c.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    check(cudaMemcpyAsync(out_host + (size_t)c.r0 * clip_samples, ws.d_o[c.slot], c.n * sizeof(Sample), cudaMemcpyDeviceToHost, s));
+    check(cudaEventRecord(ws.down[c.slot], s));
+  };
   int slot = 0;
-  long clips = 0;
-  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += clips, slot = (slot + 1) % kHostSlots) {
+  long clips = 0, index = 0;
+  for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += clips, slot = (slot + 1) % n_slots, ++index) {
     const long left = B - r0, done = r0;
     const long ramp_in = done < clips_per_chunk ? (done < 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
     const long ramp_out = left <= clips_per_chunk ? (left <= clips_per_chunk / 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
@@ -487,23 +525,38 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
     if (want < 1) want = 1;
     clips = left < want ? left : want;
     const size_t n = (size_t)clips * clip_samples;
-    cudaStream_t s = ws.st[slot];
-    check(cudaMemcpyAsync(ws.d_x[slot], x_host + (size_t)r0 * clip_samples, n * sizeof(Sample), cudaMemcpyHostToDevice, s));
+    cudaStream_t cs = ws.st[slot], ks = ws.kst[slot];
+    const bool reused = index >= n_slots;
+    if (reused) check(cudaStreamWaitEvent(cs, ws.kdone[slot], 0));  // the slot's previous kernels have read d_x
+    check(cudaMemcpyAsync(ws.d_x[slot], x_host + (size_t)r0 * clip_samples, n * sizeof(Sample), cudaMemcpyHostToDevice, cs));
+    check(cudaEventRecord(ws.up[slot], cs));
+    if (prev.live) copy_out(prev, cs);
+    prev.live = false;
+    if (rc) break;
+    check(cudaStreamWaitEvent(ks, ws.up[slot], 0));
+    if (reused) check(cudaStreamWaitEvent(ks, ws.down[slot], 0));   // the slot's previous sub-bands / output have been copied out
     if (rc) break;
     if constexpr (kPcm) {
-      rc = pqmf_analysis_pcm16(static_cast<const int16_t*>(ws.d_x[slot]), ws.d_y[slot], d_hk, d_tab, (int)clips, T, C, 0, F, M, L, flags, s);
+      rc = pqmf_analysis_pcm16(static_cast<const int16_t*>(ws.d_x[slot]), ws.d_y[slot], d_hk, d_tab, (int)clips, T, C, 0, F, M, L, flags, ks);
       if (rc) break;
-      rc = pqmf_synthesis_pcm16(ws.d_y[slot], static_cast<int16_t*>(ws.d_o[slot]), d_hk, d_tab, (int)clips, C, F, M, L, delay_frames, flags, s);
+      rc = pqmf_synthesis_pcm16(ws.d_y[slot], static_cast<int16_t*>(ws.d_o[slot]), d_hk, d_tab, (int)clips, C, F, M, L, delay_frames, flags, ks);
     } else {
-      rc = pqmf_analysis_f32(static_cast<const float*>(ws.d_x[slot]), ws.d_y[slot], d_hk, d_tab, (int)clips, T, F, M, L, flags, s);
+      rc = pqmf_analysis_f32(static_cast<const float*>(ws.d_x[slot]), ws.d_y[slot], d_hk, d_tab, (int)clips, T, F, M, L, flags, ks);
       if (rc) break;
-      rc = pqmf_synthesis_f32(ws.d_y[slot], static_cast<float*>(ws.d_o[slot]), d_hk, d_tab, (int)clips, F, M, L, delay_frames, flags, s);
+      rc = pqmf_synthesis_f32(ws.d_y[slot], static_cast<float*>(ws.d_o[slot]), d_hk, d_tab, (int)clips, F, M, L, delay_frames, flags, ks);
     }
     if (rc) break;
-    if (y_host) check(cudaMemcpyAsync(y_host + (size_t)r0 * clip_samples, ws.d_y[slot], n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    check(cudaMemcpyAsync(out_host + (size_t)r0 * clip_samples, ws.d_o[slot], n * sizeof(Sample), cudaMemcpyDeviceToHost, s));
+    check(cudaEventRecord(ws.kdone[slot], ks));
+    prev.live = true;
+    prev.slot = slot;
+    prev.r0 = r0;
+    prev.n = n;
   }
-  for (int i = 0; i < kHostSlots; ++i) check(cudaStreamSynchronize(ws.st[i]));
+  if (prev.live && rc == PQMF_OK) copy_out(prev, ws.kst[prev.slot]);  // the last chunk: straight behind its kernels
+  for (int i = 0; i < kHostSlots; ++i) {
+    check(cudaStreamSynchronize(ws.st[i]));
+    check(cudaStreamSynchronize(ws.kst[i]));
+  }
   return rc;
 }
 
@@ -936,10 +989,17 @@ void pqmf_host_release(void) {
       if (ws.d_y[i]) cudaFree(ws.d_y[i]);
       if (ws.d_o[i]) cudaFree(ws.d_o[i]);
       if (ws.streams_ready && ws.st[i]) cudaStreamDestroy(ws.st[i]);
+      if (ws.streams_ready && ws.kst[i]) cudaStreamDestroy(ws.kst[i]);
+      if (ws.streams_ready && ws.up[i]) cudaEventDestroy(ws.up[i]);
+      if (ws.streams_ready && ws.kdone[i]) cudaEventDestroy(ws.kdone[i]);
+      if (ws.streams_ready && ws.down[i]) cudaEventDestroy(ws.down[i]);
     }
     if (ws.d_bank) cudaFree(ws.d_bank);
+    if (ws.streams_ready && ws.bank_up) cudaEventDestroy(ws.bank_up);
+    ws.bank_up = nullptr;
     for (int i = 0; i < kHostSlots; ++i) {
-      ws.st[i] = nullptr;
+      ws.st[i] = ws.kst[i] = nullptr;
+      ws.up[i] = ws.kdone[i] = ws.down[i] = nullptr;
       ws.d_x[i] = ws.d_o[i] = nullptr;
       ws.d_y[i] = nullptr;
     }
