@@ -15,4 +15,4 @@ for _ in range(3): step()
 t0 = time.perf_counter()
 for _ in range(10): step()
 dt = (time.perf_counter() - t0) / 10
-print(f"chunk {os.environ.get('PQMF_HOST_CHUNK_MIB', '16')} MiB: {dt*1e3:.2f} ms per round trip of {B} x 2^20 -> {B*T/dt*1e-9:.2f} Gsamples/s, {B*T*4/dt*1e-9:.1f} GB/s each way")
+print(f"chunk {os.environ.get('PQMF_HOST_CHUNK_MIB', '8')} MiB: {dt*1e3:.2f} ms per round trip of {B} x 2^20 -> {B*T/dt*1e-9:.2f} Gsamples/s, {B*T*4/dt*1e-9:.1f} GB/s each way")
