@@ -181,7 +181,10 @@ int pqmf_reconstruct_f32(const float* x, float* out, float* scratch, size_t scra
  *      reference's .ts, README.md:16 -- would call): host buffers in, host buffers out.
  * Pipelines H2D copy, analysis, synthesis and D2H copy over row chunks on internal streams and
  * synchronises before returning.  x_host [B, T] -> y_host [B, M, T/M] (may be NULL) and
- * out_host [B, T].  Pinned host buffers give full PCIe bandwidth; pageable ones work. */
+ * out_host [B, T].  Pinned host buffers give full PCIe bandwidth; pageable ones work.
+ * Tuning knobs (environment, read once per process): PQMF_HOST_CHUNK_MIB (row-chunk size in MiB of fp32 samples, default 8),
+ * PQMF_HOST_SLOTS (chunks in flight, 2..8, default 4).  The per-device staging workspace (3 buffers per slot) is created on first use,
+ * only grows, and is freed by pqmf_host_release(). */
 int pqmf_roundtrip_host_f32(const float* x_host, float* y_host, float* out_host, const float* hk_host,
                             const float* tables_host, int B, long T, int M, int L, int delay_frames, unsigned flags,
                             int device);
