@@ -127,13 +127,8 @@ __device__ __forceinline__ void split2_f16s(float a, float b, uint32_t& h1_bits,
   h1_bits = *reinterpret_cast<const uint32_t*>(&h1);
   h2_bits = *reinterpret_cast<const uint32_t*>(&h2);
 }
-// accumulator columns -> value: 2^-10 (D0 + 2^-11 D1)
-__device__ __forceinline__ float h4_combine(uint32_t d0, uint32_t d1) {
-  return fmaf(__uint_as_float(d1), 1.0f / kH4Res, __uint_as_float(d0)) * (1.0f / (float)(1 << kH16ScaleLog2));
-}
-
-// the same for two adjacent columns as packed FP32 (one FFMA2 + one FMUL2 instead of two of each: the epilogue sits on the workers'
-// critical path); per element exactly the arithmetic of h4_combine
+// accumulator columns -> values: 2^-10 (D0 + 2^-11 D1), two adjacent columns at a time as packed FP32 (one FFMA2 + one FMUL2;
+// per element an fma and a multiplication by a power of two)
 __device__ __forceinline__ float2 h4_combine2(uint32_t d0a, uint32_t d0b, uint32_t d1a, uint32_t d1b) {
   const float2 t = __ffma2_rn(make_float2(__uint_as_float(d1a), __uint_as_float(d1b)), make_float2(1.0f / kH4Res, 1.0f / kH4Res),
                               make_float2(__uint_as_float(d0a), __uint_as_float(d0b)));
