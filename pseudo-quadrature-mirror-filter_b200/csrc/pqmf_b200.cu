@@ -445,7 +445,10 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   }();
   const long clip_samples = T * C;                      // one clip = C rows of T samples
   long clips_per_chunk = chunk_bytes / (clip_samples * (long)sizeof(float));
-  if (clips_per_chunk < 1) clips_per_chunk = 1;
+  // the Hankel kernels take calls of >= 96 tiles of 8192 samples (use_h4): no chunk, ramp chunks included, goes below that
+  const long tiles_per_clip = (long)C * ((T + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples);
+  const long min_clips = (96 + tiles_per_clip - 1) / tiles_per_clip;
+  if (clips_per_chunk < min_clips) clips_per_chunk = min_clips;
   if (clips_per_chunk > B) clips_per_chunk = B;
   const size_t chunk_elems = (size_t)clips_per_chunk * clip_samples;
   const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
@@ -522,8 +525,10 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
     const long ramp_in = done < clips_per_chunk ? (done < 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
     const long ramp_out = left <= clips_per_chunk ? (left <= clips_per_chunk / 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
     long want = ramp_in < ramp_out ? ramp_in : ramp_out;
-    if (want < 1) want = 1;
+    if (want < min_clips) want = min_clips;   // never below what the tensor-core kernels take (smaller calls run other kernels)
     clips = left < want ? left : want;
+    if (left - clips > 0 && left - clips < min_clips)   // do not leave a remainder the tensor-core kernels would refuse
+      clips = left <= clips_per_chunk ? left : left - min_clips;
     const size_t n = (size_t)clips * clip_samples;
     cudaStream_t cs = ws.st[slot], ks = ws.kst[slot];
     const bool reused = index >= n_slots;
