@@ -205,6 +205,10 @@ int pqmf_roundtrip_host_multi_f32(const float* x_host, float* y_host, float* out
 /* The row range [*start, *start + *count) of shard `shard` of `n_shards` (what pqmf_roundtrip_host_multi_f32 gives device number
  * `shard` of its list; host-only arithmetic, the same rule as the Python side's shard_rows). */
 void pqmf_shard_rows(long n_rows, int n_shards, int shard, long* start, long* count);
+/* The row-chunk schedule pqmf_roundtrip_host_f32 / _pcm16 use for B clips of C channels x T samples (host-only arithmetic): writes the
+ * clips of the first max_chunks chunks to clips[] (may be NULL) and returns the number of chunks.  Every chunk holds whole clips, at
+ * least the 96 tiles of 8192 samples the tensor-core kernels take (unless the whole call is smaller), at most one staging buffer. */
+int pqmf_host_chunk_plan(int B, long T, int C, long* clips, int max_chunks);
 
 /* Frees the per-device staging buffers / streams that the pqmf_roundtrip_host_* entry points keep between calls. */
 void pqmf_host_release(void);

@@ -417,6 +417,41 @@ bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
   return tables != nullptr && !(flags & (PQMF_FLAG_NO_SIGN | PQMF_FLAG_FOLD | PQMF_FLAG_FP32)) && h4_family(M, L);
 }
 
+// ---- chunk schedule of the host-buffer entry points (host arithmetic only; exported as pqmf_host_chunk_plan for the tests) ----
+// Chunks of ~chunk_bytes of fp32 samples, whole clips, small chunks at both ends (1/4, 1/4, 1/2 of a chunk ...: nothing overlaps the
+// first H2D copy and the last D2H copy), and never fewer clips than the 96 tiles of 8192 samples the Hankel kernels take (use_h4):
+// a smaller chunk -- or a smaller remainder at the end -- would run other kernels, slower and with different rounding.
+struct HostChunks {
+  long clips_per_chunk, min_clips;
+};
+long host_chunk_bytes() {
+  static const long v = [] {
+    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 8 MiB of fp32 samples per chunk
+    const long m = e ? atol(e) : 0;
+    return (m > 0 && m <= 1024 ? m : 8L) << 20;
+  }();
+  return v;
+}
+HostChunks host_chunks(long B, long T, int C) {
+  HostChunks h;
+  const long tiles_per_clip = (long)C * ((T + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples);
+  h.min_clips = (96 + tiles_per_clip - 1) / tiles_per_clip;
+  h.clips_per_chunk = host_chunk_bytes() / (T * C * (long)sizeof(float));
+  if (h.clips_per_chunk < h.min_clips) h.clips_per_chunk = h.min_clips;
+  if (h.clips_per_chunk > B) h.clips_per_chunk = B;
+  return h;
+}
+long host_next_chunk(const HostChunks& h, long B, long r0) {  // clips in the chunk that starts at clip r0
+  const long left = B - r0, done = r0, full = h.clips_per_chunk;
+  const long ramp_in = done < full ? (done < 2 ? full / 4 : full / 2) : full;
+  const long ramp_out = left <= full ? (left <= full / 2 ? full / 4 : full / 2) : full;
+  long want = ramp_in < ramp_out ? ramp_in : ramp_out;
+  if (want < h.min_clips) want = h.min_clips;
+  long clips = left < want ? left : want;
+  if (left - clips > 0 && left - clips < h.min_clips) clips = left <= full ? left : left - h.min_clips;  // no undersized remainder
+  return clips;
+}
+
 // ---- host-buffer round trip, generic over the sample format (float rows, or int16 interleaved WAV frames with C channels) ----
 // Row chunks of ~8 MiB of fp32 samples (2 Mi samples): the H2D copy of chunk i + 1, the two kernels of chunk i and the D2H copy of
 // chunk i - 1 overlap (PCIe is full duplex); copies and kernels have streams of their own (see the copy-phase note in the loop below).
@@ -433,23 +468,14 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return (int)e;
   const long F = T / M;
-  static const long chunk_bytes = [] {
-    const char* e = getenv("PQMF_HOST_CHUNK_MIB");   // tuning knob; default 8 MiB of fp32 samples per chunk
-    const long v = e ? atol(e) : 0;
-    return (v > 0 && v <= 1024 ? v : 8L) << 20;
-  }();
   static const int n_slots = [] {
     const char* e = getenv("PQMF_HOST_SLOTS");       // tuning knob: chunks in flight (default 4)
     const int v = e ? atoi(e) : 0;
     return v >= 2 && v <= kHostSlots ? v : 4;
   }();
   const long clip_samples = T * C;                      // one clip = C rows of T samples
-  long clips_per_chunk = chunk_bytes / (clip_samples * (long)sizeof(float));
-  // the Hankel kernels take calls of >= 96 tiles of 8192 samples (use_h4): no chunk, ramp chunks included, goes below that
-  const long tiles_per_clip = (long)C * ((T + pqmf::kH4TileSamples - 1) / pqmf::kH4TileSamples);
-  const long min_clips = (96 + tiles_per_clip - 1) / tiles_per_clip;
-  if (clips_per_chunk < min_clips) clips_per_chunk = min_clips;
-  if (clips_per_chunk > B) clips_per_chunk = B;
+  const HostChunks plan = host_chunks(B, T, C);
+  const long clips_per_chunk = plan.clips_per_chunk;
   const size_t chunk_elems = (size_t)clips_per_chunk * clip_samples;
   const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
   HostWorkspace& ws = g_host_ws[device];
@@ -496,8 +522,7 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   if (n_tab) check(cudaMemcpyAsync(d_tab, tables_host, (size_t)n_tab * sizeof(float), cudaMemcpyHostToDevice, ws.st[0]));
   check(cudaEventRecord(ws.bank_up, ws.st[0]));
   for (int i = 0; i < n_slots; ++i) check(cudaStreamWaitEvent(ws.kst[i], ws.bank_up, 0));  // no host-side wait: the first H2D copy follows at once
-  // Chunk schedule: small chunks at both ends (1/4, 1/4, 1/2 of a chunk ...) shorten the pipeline fill (nothing overlaps the first
-  // H2D) and drain (nothing overlaps the last D2H); full chunks in between keep the kernels efficient.
+  // Chunk schedule: host_chunks / host_next_chunk above.
   // Copy phase: WHEN a D2H copy starts relative to the H2D copy running beside it decides what both directions get.  With the same
   // sixteen 16 MiB copies each way and only a delay between a chunk's H2D and its D2H (tools/e2e_pipeline_probe.py), a round trip takes
   // 5.87 ms at delay 0, 6.3 - 6.7 ms when the D2H starts 5 - 65 % into the next H2D copy, ~6.0 ms at 80 - 95 % and 6.2 - 6.8 ms again
@@ -521,14 +546,7 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   int slot = 0;
   long clips = 0, index = 0;
   for (long r0 = 0; r0 < B && rc == PQMF_OK; r0 += clips, slot = (slot + 1) % n_slots, ++index) {
-    const long left = B - r0, done = r0;
-    const long ramp_in = done < clips_per_chunk ? (done < 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
-    const long ramp_out = left <= clips_per_chunk ? (left <= clips_per_chunk / 2 ? clips_per_chunk / 4 : clips_per_chunk / 2) : clips_per_chunk;
-    long want = ramp_in < ramp_out ? ramp_in : ramp_out;
-    if (want < min_clips) want = min_clips;   // never below what the tensor-core kernels take (smaller calls run other kernels)
-    clips = left < want ? left : want;
-    if (left - clips > 0 && left - clips < min_clips)   // do not leave a remainder the tensor-core kernels would refuse
-      clips = left <= clips_per_chunk ? left : left - min_clips;
+    clips = host_next_chunk(plan, B, r0);
     const size_t n = (size_t)clips * clip_samples;
     cudaStream_t cs = ws.st[slot], ks = ws.kst[slot];
     const bool reused = index >= n_slots;
@@ -946,6 +964,18 @@ int pqmf_roundtrip_host_pcm16(const int16_t* pcm_host, float* y_host, int16_t* o
                               int device) {
   if (C < 1 || C > 64) return PQMF_ERR_ARG;
   return roundtrip_host(pcm_host, y_host, out_host, hk_host, tables_host, B, T, C, M, L, delay_frames, flags, device);
+}
+
+int pqmf_host_chunk_plan(int B, long T, int C, long* clips, int max_chunks) {
+  if (B <= 0 || T <= 0 || C <= 0) return PQMF_ERR_ARG;
+  const HostChunks plan = host_chunks(B, T, C);
+  int n = 0;
+  for (long r0 = 0; r0 < B; ++n) {
+    const long c = host_next_chunk(plan, B, r0);
+    if (clips && n < max_chunks) clips[n] = c;
+    r0 += c;
+  }
+  return n;
 }
 
 void pqmf_shard_rows(long n_rows, int n_shards, int shard, long* start, long* count) {

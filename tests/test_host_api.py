@@ -205,3 +205,36 @@ def test_cabi_argument_checks_happen_before_any_cuda_call(pq):
     assert c.pqmf_roundtrip_host_multi_f32(None, None, None, None, None, 4, 64, 16, 512, 0, 0, devs, 2) == -1     # null buffers
     assert c.pqmf_roundtrip_host_pcm16(None, None, None, None, None, 4, 64, 0, 16, 512, 0, 0, 0) == -1            # zero channels
     assert b"invalid argument" in c.pqmf_strerror(-1)
+
+
+def test_host_chunk_schedule_never_undercuts_the_tensor_core_kernels():
+    """pqmf_host_chunk_plan (the schedule of pqmf_roundtrip_host_*): whole clips, every clip exactly once, no chunk -- ramp chunks and the
+    remainder included -- below the 96 tiles of 8192 samples the Hankel kernels take (unless the whole call is smaller), none above
+    the staging buffer, small chunks at the start."""
+    import ctypes
+
+    from pqmf_b200 import _lib
+
+    f = _lib.cabi.pqmf_host_chunk_plan
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_long), ctypes.c_int]
+    assert f(0, 4096, 1, None, 0) == -1 and f(4, 0, 1, None, 0) == -1 and f(4, 4096, 0, None, 0) == -1
+    shapes = [(64, 1 << 20, 1), (64, 1 << 20, 2), (40, 1 << 16, 2), (2048, 480000, 1), (7, 65536, 2), (100, 8192, 1), (1000, 4096, 1),
+              (33, 40000, 3), (5, 1 << 22, 1), (97, 70000, 1), (1, 16, 1), (3, 303104, 1), (8192, 2048, 1), (513, 131072, 2)]
+    for b, t, c in shapes:
+        n = f(b, t, c, None, 0)
+        assert n >= 1
+        buf = (ctypes.c_long * n)()
+        assert f(b, t, c, buf, n) == n
+        clips = list(buf)
+        assert sum(clips) == b and min(clips) >= 1
+        tiles_per_clip = c * -(-t // 8192)
+        need = -(-96 // tiles_per_clip)
+        if b >= need:
+            assert min(clips) >= need, (b, t, c, clips)
+        else:
+            assert clips == [b]
+        full = max((8 << 20) // (t * c * 4), need)
+        assert max(clips) <= min(full, b), (b, t, c, clips, full)
+        if n >= 8:  # long schedules start and end with small chunks (pipeline fill and drain)
+            assert clips[0] < max(clips) or full == need
