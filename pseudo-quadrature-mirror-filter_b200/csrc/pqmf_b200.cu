@@ -423,6 +423,7 @@ bool use_h4_family(int M, int L, const float* tables, unsigned flags) {
 // a smaller chunk -- or a smaller remainder at the end -- would run other kernels, slower and with different rounding.
 struct HostChunks {
   long clips_per_chunk, min_clips;
+  long buffer_clips() const { return clips_per_chunk + min_clips - 1; }  // the largest chunk: a full one plus an undersized remainder
 };
 long host_chunk_bytes() {
   static const long v = [] {
@@ -448,7 +449,7 @@ long host_next_chunk(const HostChunks& h, long B, long r0) {  // clips in the ch
   long want = ramp_in < ramp_out ? ramp_in : ramp_out;
   if (want < h.min_clips) want = h.min_clips;
   long clips = left < want ? left : want;
-  if (left - clips > 0 && left - clips < h.min_clips) clips = left <= full ? left : left - h.min_clips;  // no undersized remainder
+  if (left - clips > 0 && left - clips < h.min_clips) clips = left;  // no undersized remainder: at most full + min_clips - 1 clips (buffer_clips)
   return clips;
 }
 
@@ -476,7 +477,7 @@ int roundtrip_host(const Sample* x_host, float* y_host, Sample* out_host, const 
   const long clip_samples = T * C;                      // one clip = C rows of T samples
   const HostChunks plan = host_chunks(B, T, C);
   const long clips_per_chunk = plan.clips_per_chunk;
-  const size_t chunk_elems = (size_t)clips_per_chunk * clip_samples;
+  const size_t chunk_elems = (size_t)(plan.buffer_clips() < B ? plan.buffer_clips() : B) * clip_samples;
   const long n_tab = tables_host ? pqmf_tables_numel(M, L) : 0;
   HostWorkspace& ws = g_host_ws[device];
   std::lock_guard<std::mutex> lock(ws.mutex);

@@ -235,6 +235,37 @@ def test_host_chunk_schedule_never_undercuts_the_tensor_core_kernels():
         else:
             assert clips == [b]
         full = max((8 << 20) // (t * c * 4), need)
-        assert max(clips) <= min(full, b), (b, t, c, clips, full)
+        assert max(clips) <= min(full + need - 1, b), (b, t, c, clips, full)  # a full chunk may absorb an undersized remainder
         if n >= 8:  # long schedules start and end with small chunks (pipeline fill and drain)
             assert clips[0] < max(clips) or full == need
+
+
+def test_host_chunk_schedule_with_tiny_chunks():
+    """The same properties when PQMF_HOST_CHUNK_MIB makes a chunk no larger than the kernels' minimum (the setting is read once per
+    process: a subprocess), on random shapes: a remainder below the minimum joins the chunk before it instead of running alone."""
+    import subprocess
+    import textwrap
+
+    code = textwrap.dedent("""
+        import ctypes, random, sys
+        sys.path.insert(0, %r)
+        from pqmf_b200 import _lib
+        f = _lib.cabi.pqmf_host_chunk_plan
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_long), ctypes.c_int]
+        random.seed(7)
+        for _ in range(1500):
+            b = random.randint(1, 3000); t = random.choice((2048, 4096, 8192, 40960, 65536, 303104, 1 << 20)); c = random.choice((1, 2, 3))
+            n = f(b, t, c, None, 0)
+            buf = (ctypes.c_long * n)()
+            assert f(b, t, c, buf, n) == n
+            clips = list(buf)
+            need = -(-96 // (c * -(-t // 8192)))
+            full = max((1 << 20) // (t * c * 4), need)
+            assert sum(clips) == b
+            assert min(clips) >= need or clips == [b], (b, t, c, clips[-4:], need)
+            assert max(clips) <= min(full + need - 1, b), (b, t, c, max(clips), full, need)
+        print("ok")
+    """) % ROOT
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PQMF_HOST_CHUNK_MIB="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

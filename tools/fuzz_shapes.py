@@ -80,4 +80,29 @@ for case in range(16):
         print("PCM DOWNMIX MISMATCH", dict(m=m, c=c, t=t, clips=clips)); sys.exit(1)
     if not torch.equal(mod.reconstruct(xf), mod.process(xf)[0]):
         print("RECONSTRUCT MISMATCH", dict(m=m, c=c, t=t, clips=clips)); sys.exit(1)
+# host-buffer entry points against the device path: bit-identical whatever the chunk schedule does (tools: PQMF_HOST_CHUNK_MIB=1 makes many chunks)
+from pqmf_b200 import _lib
+for case in range(int(sys.argv[3]) if len(sys.argv) > 3 else 12):
+    m = random.choice((8, 16, 16, 32))
+    c = random.choice((1, 1, 2))
+    t = random.choice((2048, 8192, 40960, 65536, 303104, 1 << 20)) // (8 * m) * (8 * m)
+    b = random.choice((1, 3, 17, 40, 100, 257))
+    if b * c * t > (1 << 27): b = max(1, (1 << 27) // (c * t))
+    mod = pq.CachedPQMF(100, m).cuda()
+    hk_h, tab_h = mod.hk.cpu().contiguous(), mod._tables.cpu().contiguous()
+    L = mod.hk.shape[1]
+    if random.random() < 0.5:
+        x = (0.5 * torch.randn(b * c, 1, t)).clamp_(-1, 1)
+        hx = x.pin_memory(); ho = torch.empty(b * c, t).pin_memory(); hy = torch.empty(b * c, m, t // m).pin_memory()
+        rc = _lib.cabi.pqmf_roundtrip_host_f32(hx.data_ptr(), hy.data_ptr(), ho.data_ptr(), hk_h.data_ptr(), tab_h.data_ptr(), b * c, t, m, L, 1, int(mod._flags), 0)
+        y = mod(x.cuda()); o = mod.inverse(y)
+        ok = rc == 0 and torch.equal(hy, y.cpu()) and torch.equal(ho, o.cpu()[:, 0])
+    else:
+        pcm = torch.randint(-32768, 32768, (b, t, c), dtype=torch.int32).to(torch.int16)
+        hp = pcm.pin_memory(); ho = torch.empty_like(hp).pin_memory(); hy = torch.empty(b * c, m, t // m).pin_memory()
+        rc = _lib.cabi.pqmf_roundtrip_host_pcm16(hp.data_ptr(), hy.data_ptr(), ho.data_ptr(), hk_h.data_ptr(), tab_h.data_ptr(), b, t, c, m, L, 1, int(mod._flags), 0)
+        y = mod.forward_pcm16(pcm.cuda()); o = mod.inverse_pcm16(y)
+        ok = rc == 0 and torch.equal(hy, y.cpu().reshape(hy.shape)) and torch.equal(ho, o.cpu())
+    if not ok:
+        print("HOST ENTRY MISMATCH", dict(m=m, c=c, t=t, b=b, rc=rc)); sys.exit(1)
 print("fuzz ok; worst |hankel - direct| per (n_band, attenuation):", {k: (f"{v[0]:.1e}", f"{v[1]:.1e}") for k, v in sorted(worst.items())})
