@@ -56,7 +56,9 @@ extern "C" {
 #define PQMF_FLAG_TAPS(qlo, qn) (((unsigned)(qlo) << 8) | ((unsigned)(qn) << 12)) /* first kept tap / 32, kept taps / 32 */
 /* edge K-steps (analysis, synthesis) of the Hankel kernels whose fp16 correction terms are provably below 6e-6 / 1.5e-5 of
  * max|input| for this bank and are skipped; 0 keeps every term */
-#define PQMF_FLAG_H4_TRIM(ta, ts) (((unsigned)(ta) << 17) | ((unsigned)(ts) << 20))
+#define PQMF_FLAG_H4_TRIM(ta, ts) ((((unsigned)(ta) & 7u) << 17) | ((((unsigned)(ta) >> 3) & 3u) << 24) | (((unsigned)(ts) & 7u) << 20))
+#define PQMF_FLAG_H4_TRIM_A(flags) ((((flags) >> 17) & 7u) | ((((flags) >> 24) & 3u) << 3)) /* analysis: 0..31 (long banks: n_band 32 / 64) */
+#define PQMF_FLAG_H4_TRIM_S(flags) (((flags) >> 20) & 7u)                                    /* synthesis: 0..7 */
 /* the bank is too long for one SM's shared memory: the tables hold two tap ranges (TAPS describes one of them) that run as two
  * launches, the second accumulating into the output (n_band 64, long prototypes at n_band 32) */
 #define PQMF_FLAG_H4_SPLIT (1u << 23)

@@ -856,12 +856,12 @@ inline void hankel4_pair_image(const uint16_t* single /*[2 KS][128][8]*/, int ks
       }
 }
 
-// Largest number of edge K-steps (per side, <= 7) whose correction terms may be dropped: the dropped terms are bounded by
+// Largest number of edge K-steps (per side, <= max_trim) whose correction terms may be dropped: the dropped terms are bounded by
 // 2 * 2^-11 * max|input| * (sum of the |bank| entries they multiply); returns the largest trim whose bound stays <= budget.
-inline int hankel4_pick_trim(const float* hk /*[M][L]*/, int M, int L, int jlo, int kt, bool synthesis, double budget) {
+inline int hankel4_pick_trim(const float* hk /*[M][L]*/, int M, int L, int jlo, int kt, bool synthesis, double budget, int max_trim = 7) {
   const int ks = (kt + 64 - M + 15) / 16, fr = 64 / M, elo = jlo / M, ehi = (jlo + kt) / M - 1;
   int best = 0;
-  for (int trim = 1; trim <= 7 && ks - 2 * trim >= 1; ++trim) {
+  for (int trim = 1; trim <= max_trim && ks - 2 * trim >= 1; ++trim) {
     double worst = 0.0;
     for (int delta = 0; delta < fr; ++delta)
       for (int q = 0; q < M; ++q) {  // q = band (analysis) or output phase (synthesis)

@@ -183,7 +183,7 @@ void h4_taps(unsigned flags, int& jlo, int& kt) {
 
 template <int M>
 int h4_analysis_m(pqmf::H4AnalysisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
-  const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);  // exact mode: every correction term
+  const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)PQMF_FLAG_H4_TRIM_A(flags);  // exact mode: every correction term
   if (flags & PQMF_FLAG_H4_SPLIT) {  // two tap ranges, two launches; only the outer edge of each range may skip the corrections
     for (int half = 0; half < 2; ++half) {
       p.g = pqmf::h4_shape(M, jlo + half * kt, kt, true, false);
@@ -235,7 +235,7 @@ int h4_analysis(const float* x, float* y, const float* tables, int B, long T, lo
 
 template <int M>
 int h4_synthesis_m(pqmf::H4SynthesisParams p, const float* tables, int jlo, int kt, int B, int L, unsigned flags, cudaStream_t st) {
-  const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
+  const int trim = (flags & PQMF_FLAG_EXACT) ? 0 : (int)PQMF_FLAG_H4_TRIM_S(flags);
   if ((flags & PQMF_FLAG_H4_SPLIT) && p.pcm_out != nullptr) return PQMF_ERR_UNSUPPORTED;  // the second launch accumulates: not in int16
   if (flags & PQMF_FLAG_H4_SPLIT) {
     for (int half = 0; half < 2; ++half) {
@@ -307,7 +307,7 @@ int h4_analysis_stream(const float* x, float* y, const float* tables, const floa
   if (((uintptr_t)x | (uintptr_t)state_in) % 32 || ((uintptr_t)y | (uintptr_t)state_out) % 16 || L % 8 != 0) return PQMF_ERR_UNSUPPORTED;  // 256-bit loads
   pqmf::H4AnalysisStreamParams p{};
   p.x = x; p.hist_in = state_in; p.hist_out = state_out; p.y = y; p.T = T; p.B = B; p.L = L; p.parity = parity & 1;
-  p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 17) & 7u);
+  p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)PQMF_FLAG_H4_TRIM_A(flags);
   p.pad_bytes = 2 * (hist - (L - jlo));
   p.g = pqmf::h4_shape(M, jlo, kt, true, false, p.pad_bytes);
   p.s = sg;
@@ -340,7 +340,7 @@ int h4_synthesis_stream(const float* s, float* out, const float* tables, const f
   if (((uintptr_t)s | (uintptr_t)state_in | (uintptr_t)state_out) % 16 || ((uintptr_t)out % 32)) return PQMF_ERR_UNSUPPORTED;
   pqmf::H4SynthesisStreamParams p{};
   p.s = s; p.state_in = state_in; p.state_out = state_out; p.out = out; p.F = F; p.B = B; p.K = K; p.parity = parity & 1;
-  p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)((flags >> 20) & 7u);
+  p.trim_lo = p.trim_hi = (flags & PQMF_FLAG_EXACT) ? 0 : (int)PQMF_FLAG_H4_TRIM_S(flags);
   p.pad_bytes = 2 * M * (hist_frames - taps_frames);
   p.g = pqmf::h4_shape(M, jlo, kt, true, true, p.pad_bytes);
   p.sg = sg;
@@ -665,7 +665,8 @@ int pqmf_build_tables_f32(const float* hk_host, const float* h_host, int N, int 
       }
     }
     const int kt_all = split ? 2 * kt : kt;
-    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, false, kTrimBudgetAnalysis);
+    // long banks have long tails: the analysis field holds up to 31 steps per side (n_band 32: 9, n_band 64: 16 of 48 per tap range)
+    const int trim_a = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, false, kTrimBudgetAnalysis, ks - 1 < 31 ? ks - 1 : 31);
     const int trim_s = pqmf::hankel4_pick_trim(hk_host, M, L, jlo, kt_all, true, kTrimBudgetSynthesis);
     if (residual) *residual = 0.0;
     if (fast_flags) *fast_flags = PQMF_FLAG_TAPS(jlo / 32, kt / 32) | PQMF_FLAG_H4_TRIM(trim_a, trim_s) | (split ? PQMF_FLAG_H4_SPLIT : 0u);

@@ -170,7 +170,8 @@ def test_tables_exist_for_the_tensor_core_band_counts_and_degrade_gracefully():
         mod = pq.PQMF(100, m)
         assert mod._tables.numel() > 0
         assert 32 * ((mod._flags >> 8) & 15) == jlo and 32 * ((mod._flags >> 12) & 31) == kt
-        assert 0 < ((mod._flags >> 17) & 7) <= 7 and 0 < ((mod._flags >> 20) & 7) <= 7
+        trim_a = ((mod._flags >> 17) & 7) | (((mod._flags >> 24) & 3) << 3)   # PQMF_FLAG_H4_TRIM_A
+        assert 0 < trim_a <= 31 and 0 < ((mod._flags >> 20) & 7) <= 7
     for att, m in ((120, 64), (100, 2)):
         mod = pq.PQMF(att, m)
         assert mod._tables.numel() == 0 and (mod._flags >> 8) == 0
