@@ -318,6 +318,26 @@ def test_hankel4_worst_case_signals(golden, pq):
     assert np.abs(out[:, 0] - ref).max() <= TOL * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("m", (32, 64))
+def test_hankel4_worst_case_analysis_long_banks(pq, m):
+    """n_band 32 / 64 trim 9 / 16 correction steps per side (their tails are long): full-scale inputs whose signs follow one band's taps,
+    tiled with the bank's period -- what those steps drop adds up coherently -- stay within the tolerance of the fp64 closed form."""
+    mod = pq.PQMF(100, m).cuda()
+    trim_a = ((mod._flags >> 17) & 7) | (((mod._flags >> 24) & 3) << 3)
+    assert trim_a > 7
+    hk = mod.hk.cpu().numpy().astype(np.float64)
+    L = hk.shape[1]
+    b, frames = 24, 1024
+    t = m * frames
+    x = np.empty((b, 1, t), np.float32)
+    for r in range(b):
+        pat = np.sign(hk[(5 * r) % m])
+        pat[pat == 0] = 1.0
+        x[r, 0] = np.roll(np.tile(pat, t // L + 2), -(L // 2) + m * (r % 7))[:t] * (1.0 - 2.0 ** -12)
+    y = mod(dev(x)).cpu().numpy()
+    assert np.abs(y - O.analysis(x[:, 0].astype(np.float64), hk)).max() <= TOL
+
+
 def test_hankel4_full_length_bank(golden, pq):
     """attenuation 120: the prototype no longer leaves 64 zero taps on each side, so the 512-tap instantiations run."""
     g = golden("bank_M16_att120.npz")
